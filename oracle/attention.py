@@ -1,0 +1,89 @@
+"""Oracle: the ``attention`` + ``rotary`` block applied to encoded audio (secondary
+rows a11/a12 of SURVEY.md section 8; TEST INFRASTRUCTURE, see oracle/__init__.py).
+
+Only the branch that is live and deterministic in the reference is restated:
+``attention.forward(x, xa=None, mask=None, pt=None, pitch_bias=None)`` with
+``n_type="rmsnorm"`` (model.py:258-262, 302-307, 316-317) and
+``rotary.forward(x, xa, mask=None)`` (model.py:191-214).  The reference's rotary
+broadcast ``[B,H,T,hd/2] * [B,T,hd/2]`` is only well defined for B == 1
+(SURVEY.md section 8a row a12), so the batched semantics here are "B=1 applied to each
+utterance" -- the loop below is that definition.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict
+
+import torch
+import torch.nn.functional as F
+
+SD = Dict[str, torch.Tensor]
+
+
+def _rms_norm(x: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+    # nn.RMSNorm(normalized_shape, eps=None): eps = finfo(dtype).eps  (essentials.py:207)
+    return F.rms_norm(x, (x.shape[-1],), w, None)
+
+
+def rotary_freqs(head_dim: int) -> torch.Tensor:
+    """``compute_f(x=None, mask=None)`` model.py:191-194 with ``gammatone``
+    essentials.py:237-240: ``200 * (40**linspace(0,1,hd/2) * 200 / 1000) / 1000``."""
+    g = torch.pow(torch.tensor(8000.0 / 200.0), torch.linspace(0, 1, head_dim // 2)) * 200.0 / 1000
+    return 200 * g / 1000
+
+
+def rotary_apply(x: torch.Tensor, xa: torch.Tensor) -> torch.Tensor:
+    """``rotary.forward(x, xa, mask=None)`` model.py:198-214 for ONE utterance:
+    ``x [1, H, T, hd]``, ``xa [1, T, D]``.  Adjacent pairs ``(x_2j, x_2j+1)`` are a
+    complex number multiplied by ``polar(||xa_t||_2, t f_j)``."""
+    assert x.shape[0] == 1 and xa.shape[0] == 1
+    T, hd = x.shape[2], x.shape[3]
+    t = torch.arange(T, dtype=torch.float32)
+    ang = torch.einsum("i,j->ij", t, rotary_freqs(hd))            # [T, hd/2]
+    m = torch.norm(xa, dim=-1, keepdim=True)                      # [1, T, 1]
+    f = torch.polar(m.expand(1, T, hd // 2).contiguous(), ang.unsqueeze(0).contiguous())
+    xc = torch.view_as_complex(x.float().reshape(1, x.shape[1], T, hd // 2, 2).contiguous()) * f
+    return torch.view_as_real(xc).flatten(-2).type_as(x)
+
+
+def attention_forward(sd: SD, x: torch.Tensor, head: int) -> torch.Tensor:
+    """``attention.forward`` live branch, ``x [B, T, D]`` -> ``[B, T, D]``."""
+    B, T, D = x.shape
+    hd = D // head
+    scale = hd ** -0.25                                           # model.py:239
+    outs = []
+    for b in range(B):
+        xb = x[b:b + 1]
+        kv = F.linear(_rms_norm(xb, sd["kv.0.weight"]), sd["kv.1.weight"], sd["kv.1.bias"])
+        k, v = kv.view(1, T, 2, head, hd).permute(2, 0, 3, 1, 4)  # 'b c (kv h d) -> kv b h c d'
+        q = F.linear(_rms_norm(xb, sd["q.0.weight"]), sd["q.1.weight"], sd["q.1.bias"])
+        q = q.view(1, T, head, hd).transpose(1, 2)
+        q = rotary_apply(q * scale, xb)                           # model.py:303-306
+        k = rotary_apply(k * scale, xb)
+        qn, kn = _rms_norm(q, sd["ln.weight"]), _rms_norm(k, sd["ln.weight"])
+        s = torch.matmul(qn, kn.transpose(-1, -2)) / math.sqrt(hd)   # SDPA default scale, :307
+        a = torch.matmul(torch.softmax(s, dim=-1), v)
+        a = a.transpose(1, 2).reshape(1, T, D)                    # 'b h c d -> b c (h d)'
+        outs.append(F.linear(a, sd["out.1.weight"], sd["out.1.bias"]))
+    return torch.cat(outs, dim=0)
+
+
+def random_attention_state_dict(dims: int, head: int, seed: int = 0, perturb: bool = True) -> SD:
+    """Weights with the reference's key names (``attention(dims, head, layer,
+    n_type="rmsnorm")`` model.py:234-252) and default-init scales."""
+    gen = torch.Generator().manual_seed(seed)
+    hd = dims // head
+
+    def U(shape, bound):
+        return (torch.rand(shape, generator=gen) * 2 - 1) * bound
+
+    b = 1.0 / math.sqrt(dims)
+    ones = (lambda n: 1.0 + U((n,), 0.3)) if perturb else (lambda n: torch.ones(n))
+    return {
+        "q.0.weight": ones(dims), "q.1.weight": U((dims, dims), b), "q.1.bias": U((dims,), b),
+        "kv.0.weight": ones(dims), "kv.1.weight": U((2 * dims, dims), b), "kv.1.bias": U((2 * dims,), b),
+        "c.0.weight": ones(dims), "c.1.weight": U((dims, dims), b), "c.1.bias": U((dims,), b),
+        "out.1.weight": U((dims, dims), b), "out.1.bias": U((dims,), b),
+        "ln.weight": ones(hd),
+        "rot.lin.weight": U((hd // 2, dims), b), "rot.lin.bias": U((hd // 2,), b),
+    }
