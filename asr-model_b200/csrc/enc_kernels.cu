@@ -1,0 +1,439 @@
+// CUDA-core kernels of the encoder: the fp32 (1e-4) variant's GEMM, and the streaming ops
+// both variants share (layout change, LayerNorm, GLU, depthwise convs, attention, rotary).
+// All math is fp32; storage is fp32 or bf16 per tensor.  Channels-last everywhere.
+#include "enc_kernels.cuh"
+
+namespace asrb {
+
+// ------------------------------------------------------------------------------------------
+// [B][C][T] fp32 -> [B][T][CP] channels-last (+ optional log-mel floor, essentials.py:489)
+// ------------------------------------------------------------------------------------------
+template <class TO>
+__global__ void to_channels_last_kernel(float* src, TO* dst, int C, int CP, int64_t T,
+                                        const uint32_t* keys, const int32_t* lengths, int64_t n_samples,
+                                        int hop, int fix_src) {
+    extern __shared__ float tile[];                       // [C][33]
+    const int b = blockIdx.y;
+    const int64_t t0 = (int64_t)blockIdx.x * 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    float floor_s = -INFINITY;
+    int64_t Tb = T;
+    if (keys) {
+        floor_s = ((key2f(keys[b]) - 8.0f) + 4.0f) / 4.0f;
+        const int64_t len = lengths ? (int64_t)lengths[b] : n_samples;
+        Tb = 1 + len / hop;
+    }
+    float* s = src + (int64_t)b * C * T;
+    for (int c = warp; c < C; c += nwarp) {
+        const int64_t t = t0 + lane;
+        float v = 0.f;
+        if (t < T) {
+            v = s[(int64_t)c * T + t];
+            if (t < Tb && v < floor_s) { v = floor_s; if (fix_src) s[(int64_t)c * T + t] = v; }
+        }
+        tile[c * 33 + lane] = v;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 32 * CP; i += blockDim.x) {
+        const int tt = i / CP, c = i - tt * CP;
+        const int64_t t = t0 + tt;
+        if (t < T) io<TO>::st(dst + ((int64_t)b * T + t) * CP + c, c < C ? tile[c * 33 + tt] : 0.f);
+    }
+}
+
+int launch_to_channels_last(const float* src, void* dst, DType dt, int64_t B, int C, int CP, int64_t T,
+                            const uint32_t* keys, const int32_t* lengths, int64_t n_samples, int hop,
+                            bool fix_src, cudaStream_t st) {
+    dim3 grid((unsigned)((T + 31) / 32), (unsigned)B);
+    size_t smem = sizeof(float) * C * 33;
+    if (dt == DT_F32)
+        to_channels_last_kernel<float><<<grid, 256, smem, st>>>((float*)src, (float*)dst, C, CP, T, keys, lengths, n_samples, hop, fix_src);
+    else
+        to_channels_last_kernel<__nv_bfloat16><<<grid, 256, smem, st>>>((float*)src, (__nv_bfloat16*)dst, C, CP, T, keys, lengths, n_samples, hop, fix_src);
+    ASRB_LAUNCH_CHECK();
+    return ASRB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// fp32 implicit-GEMM conv (taps along T) on CUDA cores: 64x64x16 tiles, 4x4 per thread
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float apply_act(float v, int act) {
+    switch (act) {
+        case ACT_GELU: return gelu_erf(v);
+        case ACT_RELU: return fmaxf(v, 0.f);
+        case ACT_SILU: return siluf_(v);
+        case ACT_GELU_GELU: return gelu_erf(gelu_erf(v));
+        default: return v;
+    }
+}
+
+template <class TA, class TO>
+__global__ void __launch_bounds__(256)
+gemm_simt_kernel(const TA* __restrict__ A, const float* __restrict__ W, const float* __restrict__ bias,
+                 const TO* __restrict__ res, TO* __restrict__ out, int64_t T, int K, int N, int taps, int act) {
+    constexpr int BM = 64, BN = 64, BK = 16;
+    __shared__ float As[BK][BM + 4];
+    __shared__ float Ws[BK][BN + 4];
+    const int b = blockIdx.z;
+    const int64_t t0 = (int64_t)blockIdx.x * BM;
+    const int n0 = blockIdx.y * BN;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int pad = taps / 2;
+    float acc[4][4] = {};
+    const TA* Ab = A + (int64_t)b * T * K;
+    for (int tap = 0; tap < taps; ++tap) {
+        for (int k0 = 0; k0 < K; k0 += BK) {
+            for (int i = threadIdx.x; i < BM * BK; i += 256) {
+                const int r = i / BK, kk = i - r * BK;
+                const int64_t t = t0 + r + tap - pad;
+                const int k = k0 + kk;
+                As[kk][r] = (t >= 0 && t < T && k < K) ? io<TA>::ld(Ab + t * K + k) : 0.f;
+            }
+            for (int i = threadIdx.x; i < BN * BK; i += 256) {
+                const int r = i / BK, kk = i - r * BK;
+                const int n = n0 + r, k = k0 + kk;
+                Ws[kk][r] = (n < N && k < K) ? W[((int64_t)n * taps + tap) * K + k] : 0.f;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int kk = 0; kk < BK; ++kk) {
+                float a[4], w[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { a[i] = As[kk][ty * 4 + i]; w[i] = Ws[kk][tx * 4 + i]; }
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
+            }
+            __syncthreads();
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int64_t t = t0 + ty * 4 + i;
+        if (t >= T) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + tx * 4 + j;
+            if (n >= N) continue;
+            const int64_t o = ((int64_t)b * T + t) * N + n;
+            float v = acc[i][j] + (bias ? bias[n] : 0.f);
+            if (res) v += io<TO>::ld(res + o);
+            io<TO>::st(out + o, apply_act(v, act));
+        }
+    }
+}
+
+int launch_gemm_simt(const void* A, DType a_dt, const float* W, const float* bias, const void* res,
+                     void* out, DType o_dt, int64_t B, int64_t T, int K, int N, int taps, Act act,
+                     cudaStream_t st) {
+    dim3 grid((unsigned)((T + 63) / 64), (unsigned)((N + 63) / 64), (unsigned)B);
+    if (a_dt == DT_F32 && o_dt == DT_F32)
+        gemm_simt_kernel<float, float><<<grid, 256, 0, st>>>((const float*)A, W, bias, (const float*)res, (float*)out, T, K, N, taps, act);
+    else if (a_dt == DT_F32 && o_dt == DT_BF16)
+        gemm_simt_kernel<float, __nv_bfloat16><<<grid, 256, 0, st>>>((const float*)A, W, bias, (const __nv_bfloat16*)res, (__nv_bfloat16*)out, T, K, N, taps, act);
+    else if (a_dt == DT_BF16 && o_dt == DT_BF16)
+        gemm_simt_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)A, W, bias, (const __nv_bfloat16*)res, (__nv_bfloat16*)out, T, K, N, taps, act);
+    else
+        gemm_simt_kernel<__nv_bfloat16, float><<<grid, 256, 0, st>>>((const __nv_bfloat16*)A, W, bias, (const float*)res, (float*)out, T, K, N, taps, act);
+    ASRB_LAUNCH_CHECK();
+    return ASRB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// LayerNorm over the channel dim (essentials.py:102-113 / nn.LayerNorm), one warp per row
+// ------------------------------------------------------------------------------------------
+template <class T>
+__global__ void layernorm_kernel(const T* __restrict__ x, const T* __restrict__ res,
+                                 const float* __restrict__ gamma, const float* __restrict__ beta,
+                                 T* __restrict__ out, int64_t rows, int D, float eps) {
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31;
+    const T* xr = x + row * D;
+    const T* rr = res ? res + row * D : nullptr;
+    float v[32];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        const int c = i * 32 + lane;
+        v[i] = 0.f;
+        if (c < D) { v[i] = io<T>::ld(xr + c) + (rr ? io<T>::ld(rr + c) : 0.f); s += v[i]; }
+    }
+    const float mean = warp_sum(s) / (float)D;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) { const int c = i * 32 + lane; if (c < D) { const float d = v[i] - mean; q = fmaf(d, d, q); } }
+    const float rstd = rsqrtf(warp_sum(q) / (float)D + eps);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        const int c = i * 32 + lane;
+        if (c < D) io<T>::st(out + row * D + c, (v[i] - mean) * rstd * gamma[c] + beta[c]);
+    }
+}
+
+int launch_layernorm(const void* x, const void* res, const float* gamma, const float* beta, void* out,
+                     DType dt, int64_t rows, int D, float eps, cudaStream_t st) {
+    if (D > 1024) return fail(ASRB_E_ARG, "layernorm: D=%d > 1024", D);
+    const unsigned grid = (unsigned)((rows + 7) / 8);
+    if (dt == DT_F32)
+        layernorm_kernel<float><<<grid, 256, 0, st>>>((const float*)x, (const float*)res, gamma, beta, (float*)out, rows, D, eps);
+    else
+        layernorm_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)res, gamma, beta, (__nv_bfloat16*)out, rows, D, eps);
+    ASRB_LAUNCH_CHECK();
+    return ASRB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// GLU (model.py:112)
+// ------------------------------------------------------------------------------------------
+template <class T>
+__global__ void glu_kernel(const T* __restrict__ x, T* __restrict__ out, int64_t rows, int D) {
+    const int64_t total = rows * D;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / D; const int c = (int)(i - r * D);
+        const float a = io<T>::ld(x + r * 2 * D + c), g = io<T>::ld(x + r * 2 * D + D + c);
+        io<T>::st(out + i, a * (1.0f / (1.0f + expf(-g))));
+    }
+}
+
+int launch_glu(const void* x, void* out, DType dt, int64_t rows, int D, cudaStream_t st) {
+    const int64_t total = rows * D;
+    unsigned grid = (unsigned)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+    if (grid == 0) grid = 1;
+    if (dt == DT_F32) glu_kernel<float><<<grid, 256, 0, st>>>((const float*)x, (float*)out, rows, D);
+    else glu_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)out, rows, D);
+    ASRB_LAUNCH_CHECK();
+    return ASRB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Depthwise conv along T (model.py:99-101 k=15 with eval BatchNorm folded in; model.py:146
+// k=3), channels-last, two channels per thread, TT outputs per thread from a register window.
+// ------------------------------------------------------------------------------------------
+template <class T> struct pair_io;
+template <> struct pair_io<float> {
+    __device__ static float2 ld(const float* p) { return *reinterpret_cast<const float2*>(p); }
+    __device__ static void st(float* p, float2 v) { *reinterpret_cast<float2*>(p) = v; }
+};
+template <> struct pair_io<__nv_bfloat16> {
+    __device__ static float2 ld(const __nv_bfloat16* p) { return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p)); }
+    __device__ static void st(__nv_bfloat16* p, float2 v) { *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(v.x, v.y); }
+};
+
+template <class TI, class TO, int KW, int TT>
+__global__ void __launch_bounds__(128)
+dwconv_kernel(const TI* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+              TO* __restrict__ out, int64_t T, int D, int act, const float* __restrict__ pos_scales) {
+    const int c = (blockIdx.x * 128 + threadIdx.x) * 2;
+    if (c >= D) return;
+    const int b = blockIdx.z;
+    const int64_t t0 = (int64_t)blockIdx.y * TT;
+    float2 wv[KW];
+#pragma unroll
+    for (int j = 0; j < KW; ++j) wv[j] = *reinterpret_cast<const float2*>(w + (int64_t)j * D + c);
+    const float2 bv = *reinterpret_cast<const float2*>(bias + c);
+    float2 xv[TT + KW - 1];
+    const TI* xb = x + (int64_t)b * T * D + c;
+#pragma unroll
+    for (int i = 0; i < TT + KW - 1; ++i) {
+        const int64_t t = t0 - KW / 2 + i;
+        xv[i] = (t >= 0 && t < T) ? pair_io<TI>::ld(xb + t * D) : make_float2(0.f, 0.f);
+    }
+    const int half = D / 2;
+#pragma unroll
+    for (int o = 0; o < TT; ++o) {
+        const int64_t t = t0 + o;
+        if (t >= T) break;
+        float2 a = bv;
+#pragma unroll
+        for (int j = 0; j < KW; ++j) { a.x = fmaf(wv[j].x, xv[o + j].x, a.x); a.y = fmaf(wv[j].y, xv[o + j].y, a.y); }
+        a.x = apply_act(a.x, act); a.y = apply_act(a.y, act);
+        if (pos_scales) {                                   // + sinusoids(T, D)[t, c] (essentials.py:354-358)
+            const float tf = (float)t;
+            a.x += c < half ? sinf(tf * pos_scales[c]) : cosf(tf * pos_scales[c - half]);
+            a.y += (c + 1) < half ? sinf(tf * pos_scales[c + 1]) : cosf(tf * pos_scales[c + 1 - half]);
+        }
+        pair_io<TO>::st(out + ((int64_t)b * T + t) * D + c, a);
+    }
+}
+
+template <class TI, class TO>
+static int dwconv_dispatch(const void* x, const float* w, const float* bias, void* out, int64_t B, int64_t T,
+                           int D, int KW, int act, const float* pos, cudaStream_t st) {
+    constexpr int TT = 16;
+    dim3 grid((unsigned)((D / 2 + 127) / 128), (unsigned)((T + TT - 1) / TT), (unsigned)B);
+    if (KW == 15) dwconv_kernel<TI, TO, 15, TT><<<grid, 128, 0, st>>>((const TI*)x, w, bias, (TO*)out, T, D, act, pos);
+    else if (KW == 3) dwconv_kernel<TI, TO, 3, TT><<<grid, 128, 0, st>>>((const TI*)x, w, bias, (TO*)out, T, D, act, pos);
+    else return fail(ASRB_E_ARG, "dwconv: kernel width %d unsupported", KW);
+    ASRB_LAUNCH_CHECK();
+    return ASRB_OK;
+}
+
+int launch_dwconv(const void* x, DType x_dt, const float* w, const float* bias, void* out, DType o_dt,
+                  int64_t B, int64_t T, int D, int KW, Act act, const float* pos_scales, cudaStream_t st) {
+    if (D & 1) return fail(ASRB_E_ARG, "dwconv: D=%d must be even", D);
+    if (x_dt == DT_F32 && o_dt == DT_F32) return dwconv_dispatch<float, float>(x, w, bias, out, B, T, D, KW, act, pos_scales, st);
+    if (x_dt == DT_BF16 && o_dt == DT_BF16) return dwconv_dispatch<__nv_bfloat16, __nv_bfloat16>(x, w, bias, out, B, T, D, KW, act, pos_scales, st);
+    if (x_dt == DT_BF16 && o_dt == DT_F32) return dwconv_dispatch<__nv_bfloat16, float>(x, w, bias, out, B, T, D, KW, act, pos_scales, st);
+    return dwconv_dispatch<float, __nv_bfloat16>(x, w, bias, out, B, T, D, KW, act, pos_scales, st);
+}
+
+// ------------------------------------------------------------------------------------------
+// Attention on CUDA cores: 32 queries x 4 dim-slices per block, 32-key tiles in shared memory,
+// online softmax in sub-batches of 8 keys.  No mask (model.py:163 passes none).
+// ------------------------------------------------------------------------------------------
+template <class T, int HD>
+__global__ void __launch_bounds__(128)
+attention_simt_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __restrict__ v,
+                      int64_t ldq, int64_t ldk, int64_t ldv, T* __restrict__ out, int64_t Tn, int D, float scale) {
+    constexpr int DP = HD / 4, KT = 32;
+    __shared__ float Ks[KT][HD + 1];
+    __shared__ float Vs[KT][HD + 1];
+    const int b = blockIdx.z, h = blockIdx.y;
+    const int ql = threadIdx.x >> 2, part = threadIdx.x & 3;
+    const int64_t tq = (int64_t)blockIdx.x * 32 + ql;
+    const bool valid = tq < Tn;
+    float qv[DP], o[DP];
+#pragma unroll
+    for (int d = 0; d < DP; ++d) {
+        qv[d] = valid ? io<T>::ld(q + ((int64_t)b * Tn + tq) * ldq + h * HD + part * DP + d) * scale : 0.f;
+        o[d] = 0.f;
+    }
+    float m = -INFINITY, l = 0.f;
+    for (int64_t k0 = 0; k0 < Tn; k0 += KT) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < KT * HD; i += 128) {
+            const int r = i / HD, d = i - r * HD;
+            const int64_t t = k0 + r;
+            Ks[r][d] = t < Tn ? io<T>::ld(k + ((int64_t)b * Tn + t) * ldk + h * HD + d) : 0.f;
+            Vs[r][d] = t < Tn ? io<T>::ld(v + ((int64_t)b * Tn + t) * ldv + h * HD + d) : 0.f;
+        }
+        __syncthreads();
+        const int nk = (int)((Tn - k0) < KT ? (Tn - k0) : KT);
+        for (int j0 = 0; j0 < nk; j0 += 8) {
+            float s[8];
+            float mx = m;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float d0 = 0.f;
+#pragma unroll
+                for (int d = 0; d < DP; ++d) d0 = fmaf(qv[d], Ks[j0 + j][part * DP + d], d0);
+                d0 += __shfl_xor_sync(0xffffffffu, d0, 1);
+                d0 += __shfl_xor_sync(0xffffffffu, d0, 2);
+                s[j] = (j0 + j < nk) ? d0 : -INFINITY;
+                mx = fmaxf(mx, s[j]);
+            }
+            const float alpha = (m == -INFINITY) ? 0.f : expf(m - mx);
+            l *= alpha;
+#pragma unroll
+            for (int d = 0; d < DP; ++d) o[d] *= alpha;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float p = (s[j] == -INFINITY) ? 0.f : expf(s[j] - mx);
+                l += p;
+#pragma unroll
+                for (int d = 0; d < DP; ++d) o[d] = fmaf(p, Vs[j0 + j][part * DP + d], o[d]);
+            }
+            m = mx;
+        }
+    }
+    if (valid) {
+        const float inv = 1.0f / l;
+#pragma unroll
+        for (int d = 0; d < DP; ++d) io<T>::st(out + ((int64_t)b * Tn + tq) * D + h * HD + part * DP + d, o[d] * inv);
+    }
+}
+
+template <class T>
+static int attention_dispatch(const void* q, const void* k, const void* v, int64_t ldq, int64_t ldk, int64_t ldv,
+                              void* out, int64_t B, int64_t Tn, int D, int H, float scale, cudaStream_t st) {
+    const int hd = D / H;
+    dim3 grid((unsigned)((Tn + 31) / 32), (unsigned)H, (unsigned)B);
+#define ASRB_ATT(HD_) attention_simt_kernel<T, HD_><<<grid, 128, 0, st>>>((const T*)q, (const T*)k, (const T*)v, ldq, ldk, ldv, (T*)out, Tn, D, scale)
+    switch (hd) {
+        case 16: ASRB_ATT(16); break;
+        case 32: ASRB_ATT(32); break;
+        case 64: ASRB_ATT(64); break;
+        case 128: ASRB_ATT(128); break;
+        default: return fail(ASRB_E_ARG, "attention: head_dim %d unsupported (16/32/64/128)", hd);
+    }
+#undef ASRB_ATT
+    ASRB_LAUNCH_CHECK();
+    return ASRB_OK;
+}
+
+int launch_attention_simt_ex(const void* q, const void* k, const void* v, int64_t ldq, int64_t ldk, int64_t ldv,
+                             void* out, DType dt, int64_t B, int64_t T, int D, int H, float scale, cudaStream_t st) {
+    if (dt == DT_F32) return attention_dispatch<float>(q, k, v, ldq, ldk, ldv, out, B, T, D, H, scale, st);
+    return attention_dispatch<__nv_bfloat16>(q, k, v, ldq, ldk, ldv, out, B, T, D, H, scale, st);
+}
+
+int launch_attention_simt(const void* qkv, void* out, DType dt, int64_t B, int64_t T, int D, int H, float scale,
+                          cudaStream_t st) {
+    const size_t es = dt == DT_F32 ? 4 : 2;
+    const char* p = (const char*)qkv;
+    return launch_attention_simt_ex(p, p + es * D, p + es * 2 * D, 3 * D, 3 * D, 3 * D, out, dt, B, T, D, H, scale, st);
+}
+
+// ------------------------------------------------------------------------------------------
+// Secondary block: RMSNorm rows; rotary (model.py:198-214) + per-head RMSNorm (model.py:307)
+// ------------------------------------------------------------------------------------------
+__global__ void rmsnorm_kernel(const float* __restrict__ x, const float* __restrict__ w, float* __restrict__ out,
+                               int64_t rows, int D, float eps) {
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31;
+    float s = 0.f;
+    for (int c = lane; c < D; c += 32) { const float v = x[row * D + c]; s = fmaf(v, v, s); }
+    const float r = rsqrtf(warp_sum(s) / (float)D + eps);
+    for (int c = lane; c < D; c += 32) out[row * D + c] = x[row * D + c] * r * w[c];
+}
+
+int launch_rmsnorm(const float* x, const float* w, float* out, int64_t rows, int D, cudaStream_t st) {
+    rmsnorm_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(x, w, out, rows, D, 1.1920928955078125e-07f);
+    ASRB_LAUNCH_CHECK();
+    return ASRB_OK;
+}
+
+// One warp per (row = (b,t), head).  x <- rmsnorm_hd( (x * pre_scale) (*) polar(||xa_t||, t f_j) ) * ln_w
+__global__ void rotary_headnorm_kernel(float* __restrict__ x_all, int64_t ld, const float* __restrict__ xa,
+                                       const float* __restrict__ ln_w, const float* __restrict__ freqs,
+                                       int64_t rows, int64_t T, int D, int H, float pre_scale, float eps) {
+    const int64_t wid = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    const int hd = D / H;
+    const int64_t row = wid / H;
+    if (row >= rows) return;
+    const int h = (int)(wid - row * H);
+    const int64_t t = row % T;
+    float s = 0.f;
+    for (int c = lane; c < D; c += 32) { const float v = xa[row * D + c]; s = fmaf(v, v, s); }
+    const float mag = sqrtf(warp_sum(s));                       // torch.norm(xa, dim=-1) (model.py:201)
+    float* x = x_all + row * ld + h * hd;
+    float ss = 0.f;
+    for (int j = lane; j < hd / 2; j += 32) {
+        const float ang = (float)t * freqs[j];
+        float sn, cs;
+        sincosf(ang, &sn, &cs);
+        const float fr = mag * cs, fi = mag * sn;               // torch.polar(m, f)
+        const float xr = x[2 * j] * pre_scale, xi = x[2 * j + 1] * pre_scale;
+        const float yr = xr * fr - xi * fi, yi = xr * fi + xi * fr;
+        x[2 * j] = yr; x[2 * j + 1] = yi;
+        ss = fmaf(yr, yr, fmaf(yi, yi, ss));
+    }
+    const float r = rsqrtf(warp_sum(ss) / (float)hd + eps);
+    __syncwarp();
+    for (int c = lane; c < hd; c += 32) x[c] = x[c] * r * ln_w[c];
+}
+
+int launch_rotary_headnorm(float* x, int64_t ld, const float* xa, const float* ln_w, const float* freqs,
+                           int64_t B, int64_t T, int D, int H, float pre_scale, cudaStream_t st) {
+    const int64_t warps = B * T * H;
+    rotary_headnorm_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(x, ld, xa, ln_w, freqs, B * T, T, D, H,
+                                                                         pre_scale, 1.1920928955078125e-07f);
+    ASRB_LAUNCH_CHECK();
+    return ASRB_OK;
+}
+
+}  // namespace asrb

@@ -1,0 +1,73 @@
+// Launch wrappers of the encoder's CUDA-core kernels (enc_kernels.cu) and of the tcgen05
+// GEMM (gemm_tc.cu).  Activations are channels-last: [B][T][C], C contiguous.
+#pragma once
+#include "common.cuh"
+
+namespace asrb {
+
+enum Act { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2, ACT_SILU = 3, ACT_GELU_GELU = 4 };
+enum DType { DT_F32 = ASRB_F32, DT_BF16 = ASRB_BF16 };
+
+// ---- CUDA-core kernels (fp32 math; storage type per argument) ----------------------------
+
+// [B][C][T] fp32 (reference layout, model.py:150-155) -> [B][T][CP] channels-last, channels
+// >= C zero-filled.  floor_keys != NULL applies the log-mel dynamic-range floor on the fly
+// (fused pcm->hidden path; essentials.py:489) and, if fix_src, also fixes src in place.
+int launch_to_channels_last(const float* src, void* dst, DType dt, int64_t B, int C, int CP, int64_t T,
+                            const uint32_t* floor_keys, const int32_t* lengths, int64_t n_samples, int hop,
+                            bool fix_src, cudaStream_t st);
+
+// out[b,t,n] = act( sum_{tap,k} A[b, t+tap-taps/2, k] W[n][tap][k] + bias[n] (+ res[b,t,n]) )
+// A zero outside [0,T) (Conv1d padding).  FFMA, fp32 accumulate.
+int launch_gemm_simt(const void* A, DType a_dt, const float* W, const float* bias, const void* res,
+                     void* out, DType o_dt, int64_t B, int64_t T, int K, int N, int taps, Act act,
+                     cudaStream_t st);
+
+// out[r,:] = LayerNorm(x[r,:] (+ res[r,:])) * gamma + beta   (biased variance, eps)
+int launch_layernorm(const void* x, const void* res, const float* gamma, const float* beta, void* out,
+                     DType dt, int64_t rows, int D, float eps, cudaStream_t st);
+
+// GLU over the channel dim: x [rows][2D] -> out [rows][D] = x[:, :D] * sigmoid(x[:, D:])
+int launch_glu(const void* x, void* out, DType dt, int64_t rows, int D, cudaStream_t st);
+
+// Depthwise conv along T, channels-last: out[b,t,c] = act(sum_j w[j][c] x[b,t+j-KW/2,c] + bias[c]);
+// pos_scales != NULL ([D/2] table s_j) adds sinusoids(t, c) (essentials.py:354-358) after the
+// activation; out may be a different storage type than x (the encoder's final store).
+int launch_dwconv(const void* x, DType x_dt, const float* w, const float* bias, void* out, DType o_dt,
+                  int64_t B, int64_t T, int D, int KW, Act act, const float* pos_scales, cudaStream_t st);
+
+// Softmax attention, no mask: qkv [B][T][3D] (q | k | v, heads contiguous inside each) ->
+// out [B][T][D].  fp32 math on CUDA cores (the fp32 variant and small shapes).
+int launch_attention_simt(const void* qkv, void* out, DType dt, int64_t B, int64_t T, int D, int H,
+                          float scale, cudaStream_t st);
+// General form: separate q/k/v row strides (elements) so rotary / rms-normed copies can be used.
+int launch_attention_simt_ex(const void* q, const void* k, const void* v, int64_t ldq, int64_t ldk, int64_t ldv,
+                             void* out, DType dt, int64_t B, int64_t T, int D, int H, float scale,
+                             cudaStream_t st);
+
+// RMSNorm rows (nn.RMSNorm, eps = fp32 machine eps): out = x / sqrt(mean(x^2)+eps) * w
+int launch_rmsnorm(const float* x, const float* w, float* out, int64_t rows, int D, cudaStream_t st);
+// rotary (model.py:198-214) + per-head RMSNorm (model.py:307) in place on x [B*T][ld], heads at h*hd
+int launch_rotary_headnorm(float* x, int64_t ld, const float* xa, const float* ln_w, const float* freqs,
+                           int64_t B, int64_t T, int D, int H, float pre_scale, cudaStream_t st);
+
+// ---- tcgen05 / TMEM / TMA GEMM (gemm_tc.cu), bf16 operands, fp32 accumulate -----------------
+enum TcEpilogue { TC_BIAS_ACT = 0, TC_GLU = 1, TC_RES_ACT = 2, TC_LN = 3 };
+
+struct TcGemmArgs {
+    const __nv_bfloat16* A;      // [B][T][K] channels-last
+    const __nv_bfloat16* W;      // [N][taps*K] tap-major (GLU: value/gate interleaved per tile)
+    const float* bias;           // [N]
+    const __nv_bfloat16* res;    // [B][T][Nout] or NULL
+    const float* gamma;          // TC_LN
+    const float* beta;           // TC_LN
+    void* out;                   // [B][T][Nout] bf16
+    int64_t B, T;
+    int K, N, taps;
+    int epilogue; int act; float eps;
+};
+bool tc_gemm_supported(int K, int N, int epilogue);
+int  tc_glu_tile_n(int N);                    // BN the GLU weight interleave must use
+int  launch_gemm_tc(const TcGemmArgs& a, cudaStream_t st);
+
+}  // namespace asrb

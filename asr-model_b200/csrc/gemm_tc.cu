@@ -1,0 +1,496 @@
+// Persistent, warp-specialised tcgen05 GEMM / implicit k-tap conv for the encoder (sm_100a).
+//
+//   out[b,t,:] = epilogue( sum_{tap,k} A[b, t+tap-taps/2, k] * W[n][tap*K + k] )
+//
+// A is channels-last bf16 [B][T][K]; a 3-D TMA map (K, T, B) with OOB zero fill supplies the
+// conv halo (t = -1, t = T) and the ragged last tile of every utterance for free.  W is
+// bf16 [N][taps*K], K-major.  Accumulators live in TMEM (fp32).  Roles per CTA (1 CTA / SM):
+//   warp 0      TMA producer   (A box 64x128, W box 64xBN, SWIZZLE_128B, 4-6 stage ring)
+//   warp 1      MMA issuer     (one thread: tcgen05.mma cta_group::1 kind::f16, M=128, N=BN)
+//   warps 2..9  epilogue       (two column halves x four TMEM lane quadrants; thread = row)
+// Epilogues (fp32 math, bf16 store through swizzled smem + TMA store, which also clips the
+// rows past T):  bias+act | GLU | bias+residual+act | bias(+residual)+LayerNorm over the full
+// row (the row's NB chunks of BN columns sit side by side in TMEM, <= 512 columns).
+#include "enc_kernels.cuh"
+#include <cuda.h>
+
+namespace asrb {
+
+static constexpr int BM = 128;          // rows (frames) per tile = TMEM lanes
+static constexpr int BK = 64;           // bf16 per 128-byte swizzle row
+static constexpr int EPI_WARPS = 8;
+static constexpr int NUM_THREADS = 64 + EPI_WARPS * 32;
+static constexpr int STAGING_BYTES = 2 * BM * 128;      // one 128x64 bf16 chunk per column half
+
+template <int BN> struct TcCfg {
+    static constexpr int STAGES = BN == 256 ? 4 : 6;
+    static constexpr int A_BYTES = BM * BK * 2;
+    static constexpr int B_BYTES = BN * BK * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int XCH_BYTES = 2 * BM * 8;                       // LN partial sums, one float2 per row and half
+    static constexpr int SMEM = STAGES * STAGE_BYTES + STAGING_BYTES + XCH_BYTES + 128 /*barriers + tmem slot*/;
+    static_assert(SMEM <= 227 * 1024, "shared memory budget");
+};
+
+// ---------------------------------- PTX wrappers ----------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void epi_bar(int id, int threads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+// K-major, SWIZZLE_128B operand tile: 128-byte rows, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// kind::f16 instruction descriptor: D fp32, A/B bf16, both K-major, M=128, N=BN (cute::UMMA::InstrDescriptor).
+__host__ __device__ constexpr uint32_t make_idesc(int bn) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+// --------------------------------- fast epilogue math -----------------------------------
+__device__ __forceinline__ float erf_fast(float x) {            // Abramowitz-Stegun 7.1.26, |err| < 1.5e-7
+    const float ax = fabsf(x);
+    const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+    float p = fmaf(1.061405429f, t, -1.453152027f);
+    p = fmaf(p, t, 1.421413741f);
+    p = fmaf(p, t, -0.284496736f);
+    p = fmaf(p, t, 0.254829592f);
+    const float e = 1.0f - p * t * __expf(-ax * ax);
+    return copysignf(e, x);
+}
+__device__ __forceinline__ float gelu_fast(float x) { return 0.5f * x * (1.0f + erf_fast(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float sigmoid_fast(float x) { return __frcp_rn(1.0f + __expf(-x)); }
+__device__ __forceinline__ float act_fast(float v, int act) {
+    switch (act) {
+        case ACT_GELU: return gelu_fast(v);
+        case ACT_RELU: return fmaxf(v, 0.f);
+        case ACT_SILU: return v * sigmoid_fast(v);
+        case ACT_GELU_GELU: return gelu_fast(gelu_fast(v));
+        default: return v;
+    }
+}
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+
+struct TcParams {
+    const float* bias; const __nv_bfloat16* res; const float* gamma; const float* beta;
+    int T, K, N, taps, act, tiles_per_utt, m_tiles, n_chunks, n_out;
+    float eps;
+};
+
+// 32 fp32 values of one row -> 32 bf16 into the swizzled staging tile (row r, columns cb..cb+31 of 64)
+__device__ __forceinline__ void stage_store32(unsigned char* staging, int r, int cb, const float (&v)[32]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int chunk = (cb >> 3) + i;                              // 16-byte chunk index 0..7 in the 128-B row
+        uint4 q;
+        q.x = pack_bf16(v[8 * i + 0], v[8 * i + 1]); q.y = pack_bf16(v[8 * i + 2], v[8 * i + 3]);
+        q.z = pack_bf16(v[8 * i + 4], v[8 * i + 5]); q.w = pack_bf16(v[8 * i + 6], v[8 * i + 7]);
+        *reinterpret_cast<uint4*>(staging + r * 128 + ((chunk ^ (r & 7)) << 4)) = q;
+    }
+}
+__device__ __forceinline__ void add_res32(float (&v)[32], const __nv_bfloat16* rp) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const uint4 q = *reinterpret_cast<const uint4*>(rp + 8 * i);
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { const float2 f = __bfloat1622float2(h[j]); v[8 * i + 2 * j] += f.x; v[8 * i + 2 * j + 1] += f.y; }
+    }
+}
+__device__ __forceinline__ void add_vec32(float (&v)[32], const float* p) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { const float4 f = __ldg(reinterpret_cast<const float4*>(p) + i); v[4 * i] += f.x; v[4 * i + 1] += f.y; v[4 * i + 2] += f.z; v[4 * i + 3] += f.w; }
+}
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+               const __grid_constant__ CUtensorMap map_out, const TcParams p) {
+    using C = TcCfg<BN>;
+    constexpr int STAGES = C::STAGES;
+    extern __shared__ __align__(1024) unsigned char smem[];                  // SWIZZLE_128B tiles need 1024-B alignment
+    unsigned char* staging = smem + STAGES * C::STAGE_BYTES;                 // 2 x [128][128 B]
+    float2* s_xch = reinterpret_cast<float2*>(staging + STAGING_BYTES);      // [2][BM] LN partial (sum, sumsq)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(staging + STAGING_BYTES + C::XCH_BYTES);
+    // bars: full[STAGES], empty[STAGES], tfull[2], tempty[2]
+    const uint32_t bar0 = smem_u32(bars);
+    auto full_bar = [&](int s) { return bar0 + 8u * s; };
+    auto empty_bar = [&](int s) { return bar0 + 8u * (STAGES + s); };
+    auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * STAGES + a); };
+    auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * STAGES + 2 + a); };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool is_ln = EPI == TC_LN;
+    const int nbu = is_ln ? p.n_chunks : 1;                                  // chunks per unit
+    const int units = is_ln ? p.m_tiles : p.m_tiles * p.n_chunks;
+    const int acc_stages = (512 / (nbu * BN)) >= 2 ? 2 : 1;
+    const int kb_per_tap = p.K / BK;
+    const int num_kb = p.taps * kb_per_tap;
+    const int pad = p.taps / 2;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_out) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), EPI_WARPS * 32); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {                                                         // TMEM: all 512 columns
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================================ TMA producer ================================
+        if (lane == 0) {
+            int s = 0; uint32_t ph = 0;
+            for (int u = blockIdx.x; u < units; u += gridDim.x) {
+                const int m = is_ln ? u : u / p.n_chunks;
+                const int nb0 = is_ln ? 0 : u % p.n_chunks;
+                const int b = m / p.tiles_per_utt, t0 = (m % p.tiles_per_utt) * BM;
+                for (int j = 0; j < nbu; ++j) {
+                    const int n0 = (nb0 + j) * BN;
+                    for (int kb = 0; kb < num_kb; ++kb) {
+                        mbar_wait(empty_bar(s), ph ^ 1);
+                        mbar_expect_tx(full_bar(s), C::STAGE_BYTES);
+                        const int tap = kb / kb_per_tap, kc = kb - tap * kb_per_tap;
+                        const uint32_t sa = smem_u32(smem + s * C::STAGE_BYTES);
+                        tma_load_3d(sa, &map_a, kc * BK, t0 + tap - pad, b, full_bar(s));
+                        tma_load_2d(sa + C::A_BYTES, &map_w, kb * BK, n0, full_bar(s));
+                        if (++s == STAGES) { s = 0; ph ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================ MMA issuer ==================================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(BN);
+            int s = 0; uint32_t ph = 0; int it = 0;
+            for (int u = blockIdx.x; u < units; u += gridDim.x, ++it) {
+                const int a = it % acc_stages;
+                const uint32_t aph = (uint32_t)(it / acc_stages) & 1u;
+                mbar_wait(tempty_bar(a), aph ^ 1);
+                tc_fence_after();
+                for (int j = 0; j < nbu; ++j) {
+                    const uint32_t d_tmem = tmem_base + (uint32_t)((a * nbu + j) * BN);
+                    for (int kb = 0; kb < num_kb; ++kb) {
+                        mbar_wait(full_bar(s), ph);
+                        tc_fence_after();
+                        const uint32_t sa = smem_u32(smem + s * C::STAGE_BYTES);
+                        const uint64_t adesc = make_smem_desc(sa), bdesc = make_smem_desc(sa + C::A_BYTES);
+#pragma unroll
+                        for (int kk = 0; kk < BK / 16; ++kk)
+                            tc_mma(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, (uint32_t)((kb | kk) != 0));
+                        tc_commit(empty_bar(s));                              // frees the smem slot when the MMAs retire
+                        if (++s == STAGES) { s = 0; ph ^= 1; }
+                    }
+                }
+                tc_commit(tfull_bar(a));                                      // accumulator complete
+            }
+        }
+    } else {
+        // ================================ epilogue ====================================
+        const int ew = warp - 2;
+        const int quad = warp & 3;                        // TMEM lane quadrant this warp may read
+        const int half = ew >> 2;                         // column half
+        const int r = quad * 32 + lane;                   // row inside the tile
+        const bool leader = (ew & 3) == 0 && lane == 0;   // issues this half's TMA stores
+        unsigned char* stg = staging + half * (BM * 128);
+        const uint32_t stg_u32 = smem_u32(stg);
+        const int bar_id = 1 + half;
+        int it = 0;
+        for (int u = blockIdx.x; u < units; u += gridDim.x, ++it) {
+            const int m = is_ln ? u : u / p.n_chunks;
+            const int nb0 = is_ln ? 0 : u % p.n_chunks;
+            const int b = m / p.tiles_per_utt, t0 = (m % p.tiles_per_utt) * BM;
+            const int a = it % acc_stages;
+            const uint32_t aph = (uint32_t)(it / acc_stages) & 1u;
+            const bool row_ok = t0 + r < p.T;
+            const int64_t grow = (int64_t)b * p.T + t0 + r;
+            mbar_wait(tfull_bar(a), aph);
+            tc_fence_after();
+            const uint32_t acc = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(a * nbu * BN);
+
+            if (EPI == TC_LN) {
+                const int ncols = p.N / 2, c_begin = half * ncols;            // this thread's slice of the row
+                float s1 = 0.f, s2 = 0.f;
+                for (int c = c_begin; c < c_begin + ncols; c += 32) {
+                    float v[32];
+                    tmem_ld32(acc + c, v);
+                    add_vec32(v, p.bias + c);
+                    if (p.res && row_ok) add_res32(v, p.res + grow * p.N + c);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) { s1 += v[i]; s2 = fmaf(v[i], v[i], s2); }
+                }
+                s_xch[half * BM + r] = make_float2(s1, s2);
+                epi_bar(3, EPI_WARPS * 32);
+                const float2 o = s_xch[(half ^ 1) * BM + r];
+                epi_bar(3, EPI_WARPS * 32);                                   // partner has read before the next tile writes
+                const float mean = (s1 + o.x) / (float)p.N;
+                const float var = fmaxf((s2 + o.y) / (float)p.N - mean * mean, 0.f);
+                const float rstd = rsqrtf(var + p.eps);
+                for (int c = c_begin; c < c_begin + ncols; c += 64) {
+                    float v0[32], v1[32];
+                    tmem_ld32(acc + c, v0);
+                    tmem_ld32(acc + c + 32, v1);
+                    add_vec32(v0, p.bias + c); add_vec32(v1, p.bias + c + 32);
+                    if (p.res && row_ok) { add_res32(v0, p.res + grow * p.N + c); add_res32(v1, p.res + grow * p.N + c + 32); }
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        v0[i] = fmaf((v0[i] - mean) * rstd, __ldg(p.gamma + c + i), __ldg(p.beta + c + i));
+                        v1[i] = fmaf((v1[i] - mean) * rstd, __ldg(p.gamma + c + 32 + i), __ldg(p.beta + c + 32 + i));
+                    }
+                    if (leader) tma_wait_read0();
+                    epi_bar(bar_id, 128);
+                    stage_store32(stg, r, 0, v0);
+                    stage_store32(stg, r, 32, v1);
+                    fence_async_smem();
+                    epi_bar(bar_id, 128);
+                    if (leader) { tma_store_3d(&map_out, stg_u32, c, t0, b); tma_commit(); }
+                }
+            } else {
+                constexpr int OUT_PER_TILE = EPI == TC_GLU ? BN / 2 : BN;     // output columns per tile
+                constexpr int COLS = OUT_PER_TILE / 2;                        // per column half
+                const int out0 = nb0 * OUT_PER_TILE + half * COLS;            // first global output column
+                for (int cc = 0; cc < COLS; cc += 64) {
+                    float v0[32], v1[32];
+                    const int tc0 = half * COLS + cc;                         // column inside the accumulator
+                    tmem_ld32(acc + tc0, v0);
+                    tmem_ld32(acc + tc0 + 32, v1);
+                    const int gc = out0 + cc;                                 // global output column
+                    if (EPI == TC_GLU) {
+                        float g0[32], g1[32];
+                        tmem_ld32(acc + BN / 2 + tc0, g0);
+                        tmem_ld32(acc + BN / 2 + tc0 + 32, g1);
+                        const int vb = nb0 * BN + tc0;                        // packed bias index (value | gate per tile)
+                        add_vec32(v0, p.bias + vb); add_vec32(v1, p.bias + vb + 32);
+                        add_vec32(g0, p.bias + vb + BN / 2); add_vec32(g1, p.bias + vb + BN / 2 + 32);
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) { v0[i] *= sigmoid_fast(g0[i]); v1[i] *= sigmoid_fast(g1[i]); }
+                    } else {
+                        add_vec32(v0, p.bias + gc); add_vec32(v1, p.bias + gc + 32);
+                        if (EPI == TC_RES_ACT && row_ok) {
+                            add_res32(v0, p.res + grow * p.n_out + gc); add_res32(v1, p.res + grow * p.n_out + gc + 32);
+                        }
+                        if (p.act != ACT_NONE) {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) { v0[i] = act_fast(v0[i], p.act); v1[i] = act_fast(v1[i], p.act); }
+                        }
+                    }
+                    if (leader) tma_wait_read0();                             // staging free again?
+                    epi_bar(bar_id, 128);
+                    stage_store32(stg, r, 0, v0);
+                    stage_store32(stg, r, 32, v1);
+                    fence_async_smem();
+                    epi_bar(bar_id, 128);
+                    if (leader) { tma_store_3d(&map_out, stg_u32, gc, t0, b); tma_commit(); }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(tempty_bar(a));                                       // accumulator drained
+        }
+        if (leader) tma_wait_all();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
+// ------------------------------------ host side -------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+// [B][T][C] bf16 activations: dims (C, T, B), box 64 x 128 x 1, 128-byte swizzle, OOB -> 0
+static int make_act_map(CUtensorMap* m, const void* base, int64_t B, int64_t T, int C) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return fail(ASRB_E_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+    cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)T, (cuuint64_t)B};
+    cuuint64_t strides[2] = {(cuuint64_t)C * 2, (cuuint64_t)T * C * 2};
+    cuuint32_t box[3] = {64, BM, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)base, dims, strides, box, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ASRB_E_CUDA, "cuTensorMapEncodeTiled(activation C=%d T=%lld B=%lld) -> %d", C, (long long)T, (long long)B, (int)r);
+    return ASRB_OK;
+}
+static int make_w_map(CUtensorMap* m, const void* base, int N, int Ktot, int bn) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return fail(ASRB_E_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+    cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)N};
+    cuuint64_t strides[1] = {(cuuint64_t)Ktot * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)bn};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)base, dims, strides, box, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ASRB_E_CUDA, "cuTensorMapEncodeTiled(weights N=%d K=%d) -> %d", N, Ktot, (int)r);
+    return ASRB_OK;
+}
+
+static int pick_bn(int N, int epi) {
+    if (epi == TC_GLU) return 256;
+    if (epi == TC_LN) return (N % 256 == 0) ? 256 : 128;
+    return (N % 256 == 0) ? 256 : 128;
+}
+int tc_glu_tile_n(int) { return 256; }
+
+bool tc_gemm_supported(int K, int N, int epi) {
+    if (K % 64 != 0 || N % 128 != 0) return false;
+    if (epi == TC_GLU && N % 256 != 0) return false;
+    if (epi == TC_LN && N > 512) return false;
+    return true;
+}
+
+template <int BN, int EPI>
+static int launch_one(const CUtensorMap& ma, const CUtensorMap& mw, const CUtensorMap& mo, const TcParams& p, int units,
+                      cudaStream_t st) {
+    auto kern = gemm_tc_kernel<BN, EPI>;
+    ASRB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::SMEM));
+    int grid = sm_count();
+    if (grid > units) grid = units;
+    kern<<<grid, NUM_THREADS, TcCfg<BN>::SMEM, st>>>(ma, mw, mo, p);
+    ASRB_LAUNCH_CHECK();
+    return ASRB_OK;
+}
+
+int launch_gemm_tc(const TcGemmArgs& a, cudaStream_t st) {
+    if (!tc_gemm_supported(a.K, a.N, a.epilogue))
+        return fail(ASRB_E_ARG, "tcgen05 GEMM: unsupported shape K=%d N=%d epilogue=%d", a.K, a.N, a.epilogue);
+    if (a.B <= 0 || a.T <= 0) return ASRB_OK;
+    const int bn = pick_bn(a.N, a.epilogue);
+    const int n_out = a.epilogue == TC_GLU ? a.N / 2 : a.N;
+    CUtensorMap ma, mw, mo;
+    ASRB_TRY(make_act_map(&ma, a.A, a.B, a.T, a.K));
+    ASRB_TRY(make_w_map(&mw, a.W, a.N, a.taps * a.K, bn));
+    ASRB_TRY(make_act_map(&mo, a.out, a.B, a.T, n_out));
+    TcParams p;
+    p.bias = a.bias; p.res = a.res; p.gamma = a.gamma; p.beta = a.beta;
+    p.T = (int)a.T; p.K = a.K; p.N = a.N; p.taps = a.taps; p.act = a.act;
+    p.tiles_per_utt = (int)((a.T + BM - 1) / BM);
+    p.m_tiles = (int)(a.B * p.tiles_per_utt);
+    p.n_chunks = a.N / bn; p.n_out = n_out; p.eps = a.eps;
+    const int units = a.epilogue == TC_LN ? p.m_tiles : p.m_tiles * p.n_chunks;
+#define ASRB_TC(BN_, EPI_) return launch_one<BN_, EPI_>(ma, mw, mo, p, units, st)
+    if (bn == 256) {
+        switch (a.epilogue) {
+            case TC_BIAS_ACT: ASRB_TC(256, TC_BIAS_ACT);
+            case TC_GLU: ASRB_TC(256, TC_GLU);
+            case TC_RES_ACT: ASRB_TC(256, TC_RES_ACT);
+            case TC_LN: ASRB_TC(256, TC_LN);
+        }
+    } else {
+        switch (a.epilogue) {
+            case TC_BIAS_ACT: ASRB_TC(128, TC_BIAS_ACT);
+            case TC_RES_ACT: ASRB_TC(128, TC_RES_ACT);
+            case TC_LN: ASRB_TC(128, TC_LN);
+        }
+    }
+#undef ASRB_TC
+    return fail(ASRB_E_ARG, "tcgen05 GEMM: no kernel for BN=%d epilogue=%d", bn, a.epilogue);
+}
+
+}  // namespace asrb
+
+// Test hook: the kernel in isolation (include/asrb200.h).
+extern "C" int asrb_test_gemm_tc(const void* a, const void* w, const float* bias, const void* res, const float* gamma,
+                                 const float* beta, void* out, int64_t B, int64_t T, int K, int N, int taps,
+                                 int epilogue, int act, void* stream) {
+    using namespace asrb;
+    if (!a || !w || !bias || !out) return fail(ASRB_E_ARG, "asrb_test_gemm_tc: NULL tensor");
+    if (epilogue < 0 || epilogue > 3 || (taps != 1 && taps != 3)) return fail(ASRB_E_ARG, "asrb_test_gemm_tc: bad epilogue/taps");
+    ASRB_TRY(require_sm100());
+    TcGemmArgs g{};
+    g.A = (const __nv_bfloat16*)a; g.W = (const __nv_bfloat16*)w; g.bias = bias; g.res = (const __nv_bfloat16*)res;
+    g.gamma = gamma; g.beta = beta; g.out = out;
+    g.B = B; g.T = T; g.K = K; g.N = N; g.taps = taps; g.epilogue = epilogue; g.act = act; g.eps = 1e-5f;
+    return launch_gemm_tc(g, (cudaStream_t)stream);
+}

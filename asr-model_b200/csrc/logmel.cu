@@ -1,0 +1,338 @@
+// Fused log-mel front end (essentials.py:469-491 batched): framing + Hann window +
+// real FFT + |X|^2 + HTK mel projection + log10/clamp/normalise in ONE pass over the PCM.
+//
+// Data layout in HBM:  pcm [B][stride] fp32 (read once, staged in shared memory where the
+// 2.5x / 6.4x frame overlap lives);  out [B][M][T] fp32 (written once);  keys [B] uint32 --
+// order-preserving image of each utterance's running max of log10(mel).
+//
+// One block = FB consecutive frames of one utterance.  Two real frames ride one complex
+// FFT (z = a + i b); an N = R*R point FFT is two rounds of R-point DFTs held in registers
+// (R threads per FFT, R = 20 for n_fft 400, 32 for n_fft 1024) with one transpose through
+// shared memory in between.  The per-utterance dynamic-range floor (max - 8) needs the max
+// of the WHOLE utterance, so this pass writes (log10 + 4) / 4 and publishes the max with
+// one atomicMax per block; logmel_floor_kernel then raises the values below the floor
+// (monotone, so max((x+4)/4, (floor+4)/4) == (max(x, floor)+4)/4 bit for bit) and only
+// writes where something changes.
+#include "logmel.cuh"
+#include "fft_regs.cuh"
+#include <vector>
+#include <cmath>
+
+namespace asrb {
+
+struct LogmelParams {
+    const float* pcm; int64_t stride; int64_t n_samples; const int32_t* lengths;
+    int hop; int T; int M; int kmax;
+    const float* window;       // [NFFT]
+    const float2* twiddle;     // [R][R]: W_N^(k1*j) at [k1*R + j]
+    const int* mel_lo;         // [M] first bin of filter m
+    const int* mel_cnt;        // [M] taps (0 for an all-zero filter)
+    const float* mel_w;        // [M][kmax]
+    float* out;                // [B][M][T]
+    uint32_t* keys;            // [B]
+};
+
+template <int NFFT, int R, int FB>
+struct LogmelCfg {
+    static constexpr int N = NFFT;
+    static constexpr int GROUPS = FB / 2;              // complex FFTs per block
+    static constexpr int THREADS = GROUPS * R;
+    static constexpr int NB = NFFT / 2 + 1;            // one-sided bins
+    static constexpr int YSTRIDE = R * (R + 1);        // float2 per group (padded transpose)
+    static constexpr int BINS_PER_THREAD = (NB + R - 1) / R;
+    static_assert(R * R == NFFT, "two-round FFT needs n_fft = R^2");
+    static_assert(FB * NB <= GROUPS * YSTRIDE * 2, "power spectra must fit over the FFT buffer");
+};
+
+template <int NFFT, int R, int FB>
+__global__ void __launch_bounds__(LogmelCfg<NFFT, R, FB>::THREADS)
+logmel_kernel(const LogmelParams p) {
+    using C = LogmelCfg<NFFT, R, FB>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int span = (FB - 1) * p.hop + NFFT;
+    float*  s_pcm = reinterpret_cast<float*>(smem_raw);                 // [span]
+    float*  s_win = s_pcm + ((span + 3) & ~3);                          // [NFFT]
+    float2* s_tw  = reinterpret_cast<float2*>(s_win + NFFT);            // [R*R]
+    float2* s_y   = s_tw + R * R;                                       // [GROUPS][YSTRIDE]
+    float*  s_pow = reinterpret_cast<float*>(s_y);                      // aliases s_y: [FB][NB]
+    float*  s_melw = reinterpret_cast<float*>(s_y + C::GROUPS * C::YSTRIDE);   // [M][kmax]
+    int*    s_lo  = reinterpret_cast<int*>(s_melw + p.M * p.kmax);      // [M]
+    int*    s_cnt = s_lo + p.M;                                         // [M]
+    __shared__ float s_red[32];
+
+    const int tid = threadIdx.x;
+    const int b = blockIdx.y;
+    const int t0 = blockIdx.x * FB;
+    const int64_t len = p.lengths ? (int64_t)p.lengths[b] : p.n_samples;
+    const int Tb = 1 + (int)(len / p.hop);                  // valid frames of this utterance
+
+    // ---- stage constants and the PCM span (zero outside [0, len): center=True padding) ----
+    for (int i = tid; i < NFFT; i += C::THREADS) s_win[i] = p.window[i];
+    for (int i = tid; i < R * R; i += C::THREADS) s_tw[i] = p.twiddle[i];
+    for (int i = tid; i < p.M * p.kmax; i += C::THREADS) s_melw[i] = p.mel_w[i];
+    for (int i = tid; i < p.M; i += C::THREADS) { s_lo[i] = p.mel_lo[i]; s_cnt[i] = p.mel_cnt[i]; }
+    {
+        const float* src = p.pcm + (int64_t)b * p.stride;
+        const int64_t s0 = (int64_t)t0 * p.hop - NFFT / 2;
+        const bool vec_ok = ((p.stride & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.pcm) & 15) == 0) &&
+                            ((p.hop & 3) == 0);
+        if (vec_ok) {                                       // s0 is a multiple of 4 here
+            for (int i = tid * 4; i < span; i += C::THREADS * 4) {
+                int64_t s = s0 + i;
+                float4 v;
+                if (s >= 0 && s + 3 < len) {
+                    v = __ldg(reinterpret_cast<const float4*>(src + s));
+                } else {
+                    v.x = (s >= 0 && s < len) ? src[s] : 0.f;
+                    v.y = (s + 1 >= 0 && s + 1 < len) ? src[s + 1] : 0.f;
+                    v.z = (s + 2 >= 0 && s + 2 < len) ? src[s + 2] : 0.f;
+                    v.w = (s + 3 >= 0 && s + 3 < len) ? src[s + 3] : 0.f;
+                }
+                *reinterpret_cast<float4*>(s_pcm + i) = v;  // span rounded up to 4 in smem
+            }
+        } else {
+            for (int i = tid; i < span; i += C::THREADS) {
+                int64_t s = s0 + i;
+                s_pcm[i] = (s >= 0 && s < len) ? src[s] : 0.f;
+            }
+        }
+    }
+    __syncthreads();
+
+    const int g = tid / R, j = tid - g * R;
+    float2* yg = s_y + g * C::YSTRIDE;
+
+    // ---- round 1: R-point DFT over n1 of z[R n1 + j], twiddle W_N^(j k1), transpose ----
+    {
+        float2 x[R];
+        const float* fa = s_pcm + (2 * g) * p.hop;
+        const float* fb = fa + p.hop;
+#pragma unroll
+        for (int n1 = 0; n1 < R; ++n1) {
+            const int n = R * n1 + j;
+            const float w = s_win[n];
+            x[n1] = make_float2(w * fa[n], w * fb[n]);
+        }
+        SmallDFT<R>::run(x);
+        yg[j] = x[0];
+#pragma unroll
+        for (int k1 = 1; k1 < R; ++k1) yg[k1 * (R + 1) + j] = cmul(x[k1], s_tw[k1 * R + j]);
+    }
+    __syncthreads();
+
+    // ---- round 2: thread k1 = j does the R-point DFT over n2 -> Z[j + R k2] ----
+    {
+        float2 y[R];
+#pragma unroll
+        for (int n2 = 0; n2 < R; ++n2) y[n2] = yg[j * (R + 1) + n2];
+        SmallDFT<R>::run(y);
+        __syncthreads();                                    // everyone has read the transpose
+#pragma unroll
+        for (int k2 = 0; k2 < R; ++k2) yg[j + R * k2] = y[k2];
+    }
+    __syncthreads();
+
+    // ---- split the packed pair: A[k] = (Z[k] + conj Z[N-k]) / 2, B[k] = (Z[k] - conj Z[N-k]) / 2i ----
+    float pa[C::BINS_PER_THREAD], pb[C::BINS_PER_THREAD];
+#pragma unroll
+    for (int i = 0; i < C::BINS_PER_THREAD; ++i) {
+        const int k = j + R * i;
+        pa[i] = pb[i] = 0.f;
+        if (k < C::NB) {
+            const float2 z1 = yg[k];
+            const float2 z2 = yg[(NFFT - k) % NFFT];
+            const float ar = z1.x + z2.x, ai = z1.y - z2.y;     // 2 Re A, 2 Im A
+            const float br = z1.y + z2.y, bi = z2.x - z1.x;     // 2 Re B, 2 Im B
+            pa[i] = 0.25f * fmaf(ar, ar, ai * ai);
+            pb[i] = 0.25f * fmaf(br, br, bi * bi);
+        }
+    }
+    __syncthreads();                                        // Z is dead: reuse it for |X|^2
+#pragma unroll
+    for (int i = 0; i < C::BINS_PER_THREAD; ++i) {
+        const int k = j + R * i;
+        if (k < C::NB) {
+            s_pow[(2 * g) * C::NB + k] = pa[i];
+            s_pow[(2 * g + 1) * C::NB + k] = pb[i];
+        }
+    }
+    __syncthreads();
+
+    // ---- banded mel projection + log10 + (x+4)/4; lane -> frame so stores are coalesced ----
+    constexpr int FW = FB < 32 ? FB : 32;                   // frames handled by one warp pass
+    constexpr int MSUB = 32 / FW;                           // filters handled side by side
+    const int lane = tid & 31, warp = tid >> 5;
+    const int nwarp = C::THREADS / 32;
+    const int f = lane % FW;
+    float vmax = -INFINITY;
+    for (int fbase = 0; fbase < FB; fbase += FW) {
+        const int fr = fbase + f;
+        const int t = t0 + fr;
+        const float* pw = s_pow + fr * C::NB;
+        for (int m = warp * MSUB + lane / FW; m < p.M; m += nwarp * MSUB) {
+            const int lo = s_lo[m], cnt = s_cnt[m];
+            const float* w = s_melw + m * p.kmax;
+            float acc = 0.f;
+            for (int i = 0; i < cnt; ++i) acc = fmaf(w[i], pw[lo + i], acc);
+            const float lg = log10f(fmaxf(acc, 1e-10f));                    // essentials.py:488
+            if (t < p.T) {
+                float s = 0.f;                                              // DataCollator pad value
+                if (t < Tb) { vmax = fmaxf(vmax, lg); s = (lg + 4.0f) / 4.0f; }   // essentials.py:490
+                p.out[((int64_t)b * p.M + m) * p.T + t] = s;
+            }
+        }
+    }
+    vmax = warp_max(vmax);
+    if (lane == 0) s_red[warp] = vmax;
+    __syncthreads();
+    if (warp == 0) {
+        float v = lane < nwarp ? s_red[lane] : -INFINITY;
+        v = warp_max(v);
+        if (lane == 0 && v > -INFINITY) atomicMax(p.keys + b, f2key(v));
+    }
+}
+
+// essentials.py:489: log_mel = maximum(log_mel, log_mel.max() - 8.0), applied in the
+// normalised domain.  Touches memory only where the floor is active.
+__global__ void logmel_floor_kernel(float* out, const uint32_t* keys, const int32_t* lengths,
+                                    int64_t n_samples, int hop, int M, int T) {
+    const int b = blockIdx.y;
+    const int64_t len = lengths ? (int64_t)lengths[b] : n_samples;
+    const int Tb = 1 + (int)(len / hop);
+    const float floor_s = ((key2f(keys[b]) - 8.0f) + 4.0f) / 4.0f;
+    float* o = out + (int64_t)b * M * T;
+    const int64_t total = (int64_t)M * T;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int t = (int)(i % T);
+        if (t < Tb) {
+            const float v = o[i];
+            if (v < floor_s) o[i] = floor_s;
+        }
+    }
+}
+
+}  // namespace asrb
+
+using namespace asrb;
+
+
+extern "C" int asrb_logmel_plan_create(int n_fft, int hop, int n_mels, const float* window_host,
+                                       const float* fbank_host, asrb_logmel_plan** plan) {
+    if (!plan || !window_host || !fbank_host) return fail(ASRB_E_ARG, "asrb_logmel_plan_create: NULL argument");
+    if (n_fft != 400 && n_fft != 1024)
+        return fail(ASRB_E_ARG, "asrb_logmel_plan_create: n_fft=%d unsupported (400 or 1024)", n_fft);
+    if (hop <= 0 || hop > n_fft || n_mels <= 0 || n_mels > 1024)
+        return fail(ASRB_E_ARG, "asrb_logmel_plan_create: bad hop=%d / n_mels=%d", hop, n_mels);
+    ASRB_TRY(require_sm100());
+    const int R = n_fft == 400 ? 20 : 32;
+    const int F = n_fft / 2 + 1;
+    // dense [F][M] -> band per filter (triangles have contiguous support)
+    std::vector<int> lo(n_mels, 0), cnt(n_mels, 0);
+    int kmax = 1;
+    for (int m = 0; m < n_mels; ++m) {
+        int first = -1, last = -1;
+        for (int f = 0; f < F; ++f)
+            if (fbank_host[(size_t)f * n_mels + m] != 0.0f) { if (first < 0) first = f; last = f; }
+        if (first >= 0) { lo[m] = first; cnt[m] = last - first + 1; if (cnt[m] > kmax) kmax = cnt[m]; }
+    }
+    std::vector<float> w((size_t)n_mels * kmax, 0.f);
+    for (int m = 0; m < n_mels; ++m)
+        for (int i = 0; i < cnt[m]; ++i) w[(size_t)m * kmax + i] = fbank_host[(size_t)(lo[m] + i) * n_mels + m];
+    std::vector<float2> tw((size_t)R * R);
+    for (int k1 = 0; k1 < R; ++k1)
+        for (int j = 0; j < R; ++j) {
+            const double a = -2.0 * M_PI * (double)(k1 * j) / (double)n_fft;
+            tw[(size_t)k1 * R + j] = make_float2((float)cos(a), (float)sin(a));
+        }
+    asrb_logmel_plan* pl = new asrb_logmel_plan{n_fft, hop, n_mels, kmax, R, nullptr, nullptr, nullptr, nullptr, nullptr};
+    auto up = [&](void** dst, const void* src, size_t bytes) -> cudaError_t {
+        cudaError_t e = cudaMalloc(dst, bytes);
+        if (e != cudaSuccess) return e;
+        return cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice);
+    };
+    cudaError_t e = up((void**)&pl->d_window, window_host, sizeof(float) * n_fft);
+    if (e == cudaSuccess) e = up((void**)&pl->d_twiddle, tw.data(), sizeof(float2) * tw.size());
+    if (e == cudaSuccess) e = up((void**)&pl->d_lo, lo.data(), sizeof(int) * n_mels);
+    if (e == cudaSuccess) e = up((void**)&pl->d_cnt, cnt.data(), sizeof(int) * n_mels);
+    if (e == cudaSuccess) e = up((void**)&pl->d_w, w.data(), sizeof(float) * w.size());
+    if (e != cudaSuccess) {
+        asrb_logmel_plan_destroy(pl);
+        return fail(ASRB_E_CUDA, "asrb_logmel_plan_create: upload failed: %s", cudaGetErrorString(e));
+    }
+    *plan = pl;
+    return ASRB_OK;
+}
+
+extern "C" void asrb_logmel_plan_destroy(asrb_logmel_plan* pl) {
+    if (!pl) return;
+    cudaFree(pl->d_window); cudaFree(pl->d_twiddle); cudaFree(pl->d_lo); cudaFree(pl->d_cnt); cudaFree(pl->d_w);
+    delete pl;
+}
+
+extern "C" int64_t asrb_logmel_num_frames(const asrb_logmel_plan* pl, int64_t n) {
+    return pl && n >= 0 ? 1 + n / pl->hop : -1;
+}
+
+extern "C" size_t asrb_logmel_workspace_bytes(const asrb_logmel_plan* pl, int64_t batch, int64_t) {
+    if (!pl || batch < 0) return 0;
+    return align_up(sizeof(uint32_t) * (size_t)(batch > 0 ? batch : 1), 256);
+}
+
+namespace asrb {
+
+template <int NFFT, int R, int FB>
+static int launch_logmel(const asrb_logmel_plan* pl, LogmelParams p, int64_t batch, cudaStream_t st) {
+    using C = LogmelCfg<NFFT, R, FB>;
+    const int span = (FB - 1) * pl->hop + NFFT;
+    size_t smem = sizeof(float) * (((span + 3) & ~3) + NFFT) + sizeof(float2) * (R * R + C::GROUPS * C::YSTRIDE) +
+                  sizeof(float) * (size_t)pl->n_mels * pl->kmax + sizeof(int) * 2 * pl->n_mels;
+    if (smem > 227 * 1024) return fail(ASRB_E_ARG, "asrb_logmel_f32: hop/n_mels need %zu B of shared memory", smem);
+    auto kern = logmel_kernel<NFFT, R, FB>;
+    ASRB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((p.T + FB - 1) / FB, (unsigned)batch);
+    kern<<<grid, C::THREADS, smem, st>>>(p);
+    ASRB_LAUNCH_CHECK();
+    return ASRB_OK;
+}
+
+// Shared by asrb_logmel_f32 and the fused pcm->hidden path: pass 1 only (values + keys).
+int logmel_pass1(const asrb_logmel_plan* pl, const float* pcm, int64_t batch, int64_t n_samples,
+                 int64_t stride, const int32_t* lengths, float* out, uint32_t* keys, cudaStream_t st) {
+    LogmelParams p;
+    p.pcm = pcm; p.stride = stride; p.n_samples = n_samples; p.lengths = lengths;
+    p.hop = pl->hop; p.T = (int)(1 + n_samples / pl->hop); p.M = pl->n_mels; p.kmax = pl->kmax;
+    p.window = pl->d_window; p.twiddle = pl->d_twiddle; p.mel_lo = pl->d_lo; p.mel_cnt = pl->d_cnt;
+    p.mel_w = pl->d_w; p.out = out; p.keys = keys;
+    ASRB_CUDA(cudaMemsetAsync(keys, 0, sizeof(uint32_t) * batch, st));
+    if (pl->n_fft == 400) return launch_logmel<400, 20, 32>(pl, p, batch, st);
+    return launch_logmel<1024, 32, 16>(pl, p, batch, st);
+}
+
+}  // namespace asrb
+
+extern "C" int asrb_logmel_f32(const asrb_logmel_plan* pl, const float* pcm, int64_t batch, int64_t n_samples,
+                               int64_t pcm_stride, const int32_t* lengths, float* out,
+                               void* ws, size_t ws_bytes, void* stream) {
+    if (!pl) return fail(ASRB_E_ARG, "asrb_logmel_f32: NULL plan");
+    if (batch < 0 || n_samples < 0 || pcm_stride < n_samples)
+        return fail(ASRB_E_ARG, "asrb_logmel_f32: bad shape batch=%lld n=%lld stride=%lld",
+                    (long long)batch, (long long)n_samples, (long long)pcm_stride);
+    if (batch == 0) return ASRB_OK;
+    if (batch > 65535) return fail(ASRB_E_ARG, "asrb_logmel_f32: batch %lld > 65535", (long long)batch);
+    if (!out || (!pcm && n_samples > 0)) return fail(ASRB_E_ARG, "asrb_logmel_f32: NULL tensor");
+    if (1 + n_samples / pl->hop > 0x7fffffff / 2) return fail(ASRB_E_ARG, "asrb_logmel_f32: too many frames");
+    if (!ws || ws_bytes < asrb_logmel_workspace_bytes(pl, batch, n_samples) || ((uintptr_t)ws & 3))
+        return fail(ASRB_E_WORKSPACE, "asrb_logmel_f32: workspace too small or NULL (%zu B given)", ws_bytes);
+    ASRB_TRY(require_sm100());
+    cudaStream_t st = (cudaStream_t)stream;
+    uint32_t* keys = (uint32_t*)ws;
+    ASRB_TRY(logmel_pass1(pl, pcm, batch, n_samples, pcm_stride, lengths, out, keys, st));
+    const int T = (int)(1 + n_samples / pl->hop);
+    const int64_t per = (int64_t)pl->n_mels * T;
+    int gx = (int)((per + 256 * 8 - 1) / (256 * 8));
+    if (gx < 1) gx = 1;
+    logmel_floor_kernel<<<dim3(gx, (unsigned)batch), 256, 0, st>>>(out, keys, lengths, n_samples, pl->hop, pl->n_mels, T);
+    ASRB_LAUNCH_CHECK();
+    return ASRB_OK;
+}

@@ -1,0 +1,16 @@
+// Internal view of the front-end plan, shared by logmel.cu and the fused pcm->hidden path.
+#pragma once
+#include "common.cuh"
+
+struct asrb_logmel_plan {
+    int n_fft, hop, n_mels, kmax, radix;
+    float* d_window; float2* d_twiddle; int* d_lo; int* d_cnt; float* d_w;
+};
+
+namespace asrb {
+// Pass 1 of the front end: out = (log10(max(mel,1e-10)) + 4) / 4 without the dynamic-range
+// floor, keys[b] = order-preserving image of max_t,m log10(mel).  The floor is applied by
+// logmel_floor_kernel (asrb_logmel_f32) or on the fly by launch_to_channels_last.
+int logmel_pass1(const asrb_logmel_plan* pl, const float* pcm, int64_t batch, int64_t n_samples,
+                 int64_t stride, const int32_t* lengths, float* out, uint32_t* keys, cudaStream_t st);
+}

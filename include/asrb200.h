@@ -1,0 +1,168 @@
+/* asrb200.h -- C ABI of libasrb200.so: the B200 (sm_100a) implementation of the
+ * log-mel front end and AudioEncoder forward of sine2pi/ASR-model.
+ *
+ * The reference has no FFI of its own (it is pure Python); each entry point below
+ * names the reference interface it replaces.  A binding (ctypes, cffi, pybind, cgo...)
+ * passes plain device/host pointers and sizes -- no torch types cross this boundary.
+ *
+ * Conventions
+ *   - every call returns int: 0 = OK, negative = error (ASRB_E_*); the message is
+ *     available from asrb_last_error() (thread-local, valid until the next call);
+ *   - nothing here throws, and the compute calls never allocate or free device memory:
+ *     tensors are caller-owned, scratch comes from an explicit workspace whose size the
+ *     *_workspace_bytes() functions report (create/destroy calls own the constants
+ *     they upload);
+ *   - compute calls are asynchronous on the given stream (a cudaStream_t passed as
+ *     void*; NULL = the legacy default stream) and are CUDA-graph capturable;
+ *   - a handle may be used from one stream at a time; there is no mutable global state;
+ *   - there is NO CPU fallback and no other GPU architecture: a device whose compute
+ *     capability is not 10.x yields ASRB_E_DEVICE.
+ */
+#ifndef ASRB200_H_
+#define ASRB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ASRB_VERSION 100          /* 0.1.0 */
+
+#define ASRB_OK            0
+#define ASRB_E_ARG        -1      /* bad argument (NULL, shape, unsupported size)      */
+#define ASRB_E_DEVICE     -2      /* not an sm_100 device / no CUDA device              */
+#define ASRB_E_WORKSPACE  -3      /* workspace NULL, misaligned or too small            */
+#define ASRB_E_CUDA       -4      /* a CUDA runtime / driver call failed                */
+#define ASRB_E_WEIGHTS    -5      /* a required state_dict tensor is missing / misshaped*/
+
+#define ASRB_F32   0
+#define ASRB_BF16  1
+
+int         asrb_version(void);
+const char* asrb_last_error(void);
+/* ASRB_OK iff `device` (ordinal) is a compute-capability 10.x GPU. */
+int         asrb_device_check(int device);
+
+/* ------------------------------------------------------------------------------------
+ * Front end.  Replaces the spectrogram branch of extract_features
+ * (essentials.py:469-491: torchaudio MelSpectrogram -> clamp(1e-10).log10() ->
+ * maximum(x, x.max()-8) -> (x+4)/4) and the zero right-padding of DataCollator
+ * (essentials.py:555-572), batched.
+ *
+ * The plan holds the constants the reference rebuilds on every call: the window
+ * (essentials.py:480, `window_fn=torch.hann_window`) and the HTK filterbank
+ * (ta:functional/functional.py:518-587).  They are passed in as HOST arrays so the
+ * binding can build them with the very torch ops the reference uses (bit-equal
+ * constants); the plan converts the dense [n_fft/2+1, n_mels] filterbank to its banded
+ * form and uploads it.  Supported n_fft: 400, 1024 (hop and n_mels are free).
+ * ---------------------------------------------------------------------------------- */
+typedef struct asrb_logmel_plan asrb_logmel_plan;
+
+int  asrb_logmel_plan_create(int n_fft, int hop, int n_mels,
+                             const float* window_host,   /* [n_fft]                    */
+                             const float* fbank_host,    /* [n_fft/2+1][n_mels]        */
+                             asrb_logmel_plan** plan);
+void asrb_logmel_plan_destroy(asrb_logmel_plan* plan);
+
+/* Frames produced for n samples: 1 + n / hop (center=True, essentials.py:478). */
+int64_t asrb_logmel_num_frames(const asrb_logmel_plan* plan, int64_t n_samples);
+size_t  asrb_logmel_workspace_bytes(const asrb_logmel_plan* plan, int64_t batch, int64_t n_samples);
+
+/* pcm   [batch][pcm_stride] fp32 device, n_samples valid columns (|x| <= 1 like load_wave)
+ * lengths  NULL, or [batch] int32 device: valid samples per utterance (<= n_samples);
+ *          frames past 1 + len/hop are written as 0.0 (DataCollator's pad value)
+ * out   [batch][n_mels][T] fp32 device, T = asrb_logmel_num_frames(n_samples)
+ * The dynamic-range floor uses the maximum over each utterance, never over the batch. */
+int asrb_logmel_f32(const asrb_logmel_plan* plan,
+                    const float* pcm, int64_t batch, int64_t n_samples, int64_t pcm_stride,
+                    const int32_t* lengths,
+                    float* out,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Encoder.  Replaces AudioEncoder.__init__/forward (model.py:120-169) with norm=False:
+ * conv stem, `layer` x [GELU, weight-normed Conv1d k3, channel LayerNorm, ConvLite, GELU,
+ * depthwise k3, GELU], + sinusoids, optional nn.TransformerEncoderLayer (enc=1).
+ *
+ * Weights are handed over as the reference's own state_dict: parallel arrays of key
+ * names, HOST fp32 pointers and element counts (SURVEY.md 8b lists the keys).  create()
+ * folds weight-norm and eval-mode BatchNorm, repacks for the tensor-core kernels and
+ * uploads; integer entries (num_batches_tracked) are ignored.
+ * ---------------------------------------------------------------------------------- */
+typedef struct asrb_encoder asrb_encoder;
+
+typedef struct asrb_encoder_config {
+    int32_t mels;        /* input channels of conv1 (80 | 128)                         */
+    int32_t dims;        /* D; multiple of 64 for ASRB_BF16                            */
+    int32_t head;        /* heads of the optional TransformerEncoderLayer              */
+    int32_t layer;       /* number of conv blocks                                      */
+    int32_t enc;         /* 1 = TransformerEncoderLayer present (model.py:138)         */
+    int32_t ffn;         /* its feed-forward width (2048 in the reference)             */
+    int32_t compute;     /* ASRB_BF16: tcgen05 bf16 operands, fp32 accumulate;         */
+                         /* ASRB_F32 : fp32 FFMA everywhere (the 1e-4 variant)         */
+    int32_t reserved;
+} asrb_encoder_config;
+
+int  asrb_encoder_create(const asrb_encoder_config* cfg, int n_tensors,
+                         const char* const* names, const float* const* host_data,
+                         const int64_t* numels, asrb_encoder** enc);
+void asrb_encoder_destroy(asrb_encoder* enc);
+size_t asrb_encoder_workspace_bytes(const asrb_encoder* enc, int64_t batch, int64_t frames);
+
+/* x    [batch][in_ch][frames] fp32 device; in_ch = mels selects conv1, in_ch = 1 selects
+ *      conv2 (model.py:152-155)
+ * out  [batch][frames][dims] device, out_dtype = ASRB_F32 | ASRB_BF16 */
+int asrb_encoder_forward(asrb_encoder* enc, const float* x, int64_t batch, int32_t in_ch,
+                         int64_t frames, void* out, int out_dtype,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* Fused hot path: PCM -> log-mel -> encoder without materialising the fp32 [B,M,T]
+ * feature tensor unless `logmel_out` is non-NULL.  Equivalent to
+ * asrb_logmel_f32 followed by asrb_encoder_forward. */
+size_t asrb_pcm_to_hidden_workspace_bytes(const asrb_logmel_plan* plan, const asrb_encoder* enc,
+                                          int64_t batch, int64_t n_samples);
+int asrb_pcm_to_hidden(const asrb_logmel_plan* plan, asrb_encoder* enc,
+                       const float* pcm, int64_t batch, int64_t n_samples, int64_t pcm_stride,
+                       const int32_t* lengths, float* logmel_out /* may be NULL */,
+                       void* out, int out_dtype,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Secondary: the `attention` block's live branch applied to encoded audio
+ * (model.py:234-317 with n_type="rmsnorm", xa=None, mask=None) including `rotary`
+ * (model.py:171-214).  Batched = the reference's B=1 semantics per utterance.
+ * Keys: q.0.weight q.1.weight q.1.bias kv.0.weight kv.1.weight kv.1.bias out.1.weight
+ * out.1.bias ln.weight (c.* and rot.lin.* are unused by the live branch).
+ * ---------------------------------------------------------------------------------- */
+typedef struct asrb_attention asrb_attention;
+
+int  asrb_attention_create(int32_t dims, int32_t head, int compute, int n_tensors,
+                           const char* const* names, const float* const* host_data,
+                           const int64_t* numels, asrb_attention** att);
+void asrb_attention_destroy(asrb_attention* att);
+size_t asrb_attention_workspace_bytes(const asrb_attention* att, int64_t batch, int64_t frames);
+/* x, out: [batch][frames][dims] fp32 device */
+int asrb_attention_forward(asrb_attention* att, const float* x, int64_t batch, int64_t frames,
+                           float* out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Test hooks (exported so the GPU unit tests can check building blocks in isolation
+ * through the same ABI; not needed by an integration).
+ * ---------------------------------------------------------------------------------- */
+/* The tcgen05/TMEM/TMA implicit-GEMM in isolation:
+ *   out[b,t,:] = epilogue( sum_{tap,k} a[b, t+tap-taps/2, k] * w[n][tap*K + k] + bias[n] )
+ * a [B][T][K] bf16, w [N][taps*K] bf16, out [B][T][N or N/2] bf16, res (or NULL) like out.
+ * epilogue: 0 bias+act | 1 GLU (w rows interleaved [128 value | 128 gate] per 256) |
+ *           2 bias+res+act | 3 bias(+res)+LayerNorm(gamma, beta, eps=1e-5).
+ * act: 0 none | 1 GELU | 2 ReLU | 3 SiLU | 4 GELU(GELU).  K % 64 == 0, N % 128 == 0. */
+int asrb_test_gemm_tc(const void* a, const void* w, const float* bias, const void* res,
+                      const float* gamma, const float* beta, void* out,
+                      int64_t B, int64_t T, int K, int N, int taps, int epilogue, int act,
+                      void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ASRB200_H_ */
