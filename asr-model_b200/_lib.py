@@ -45,6 +45,10 @@ SYMBOLS = {
     "asrb_attention_destroy": (None, [_vp]),
     "asrb_attention_workspace_bytes": (_sz, [_vp, _i64, _i64]),
     "asrb_attention_forward": (_int, [_vp, _vp, _i64, _i64, _vp, _vp, _sz, _vp]),
+    "asrb_profile_begin": (_int, []),
+    "asrb_profile_end": (_int, []),
+    "asrb_profile_get": (_int, [_int, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.POINTER(C.c_double),
+                                C.POINTER(C.c_double)]),
     "asrb_test_gemm_tc": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _int, _int, _int, _int, _int, _vp]),
 }
 
@@ -92,3 +96,17 @@ def state_dict_arrays(sd):
         nums.append(t.numel())
     n = len(names)
     return (n, (C.c_char_p * n)(*names), (C.c_void_p * n)(*ptrs), (_i64 * n)(*nums), keep)
+
+
+def profile_records():
+    """Stop profiling and return [(tag, ms, flops, bytes), ...] in launch order."""
+    lib = load()
+    n = lib.asrb_profile_end()
+    if n < 0:
+        check(n, "asrb_profile_end")
+    out = []
+    for i in range(n):
+        tag, ms, fl, by = C.c_char_p(), C.c_float(), C.c_double(), C.c_double()
+        check(lib.asrb_profile_get(i, C.byref(tag), C.byref(ms), C.byref(fl), C.byref(by)), "asrb_profile_get")
+        out.append((tag.value.decode(), ms.value, fl.value, by.value))
+    return out

@@ -29,6 +29,20 @@ inline int fail(int code, const char* fmt, ...) {
 int require_sm100();                       // api.cu: current device must be cc 10.x
 int sm_count();                            // api.cu: SM count of the current device (cached)
 
+// ---- optional per-launch profiler (asrb_profile_*): CUDA events around every kernel launch
+// on the launching stream, with the launch's algorithmic flops / bytes.  Off by default. ----
+struct ProfRec { const char* tag; cudaEvent_t e0, e1; double flops, bytes; };
+bool prof_on();
+void prof_push(const char* tag, cudaStream_t st, double flops, double bytes);   // records e0
+void prof_pop(cudaStream_t st);                                                 // records e1
+struct ProfScope {
+    cudaStream_t st; bool on;
+    ProfScope(const char* tag, cudaStream_t s, double flops, double bytes) : st(s), on(prof_on()) {
+        if (on) prof_push(tag, st, flops, bytes);
+    }
+    ~ProfScope() { if (on) prof_pop(st); }
+};
+
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // Bump allocator over the caller's workspace.

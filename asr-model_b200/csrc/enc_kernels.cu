@@ -44,6 +44,7 @@ __global__ void to_channels_last_kernel(float* src, TO* dst, int C, int CP, int6
 int launch_to_channels_last(const float* src, void* dst, DType dt, int64_t B, int C, int CP, int64_t T,
                             const uint32_t* keys, const int32_t* lengths, int64_t n_samples, int hop,
                             bool fix_src, cudaStream_t st) {
+    ProfScope ps("to_channels_last", st, 0.0, (double)B * T * (4.0 * C + (dt == DT_F32 ? 4.0 : 2.0) * CP));
     dim3 grid((unsigned)((T + 31) / 32), (unsigned)B);
     size_t smem = sizeof(float) * C * 33;
     if (dt == DT_F32)
@@ -127,6 +128,7 @@ gemm_simt_kernel(const TA* __restrict__ A, const float* __restrict__ W, const fl
 int launch_gemm_simt(const void* A, DType a_dt, const float* W, const float* bias, const void* res,
                      void* out, DType o_dt, int64_t B, int64_t T, int K, int N, int taps, Act act,
                      cudaStream_t st) {
+
     dim3 grid((unsigned)((T + 63) / 64), (unsigned)((N + 63) / 64), (unsigned)B);
     if (a_dt == DT_F32 && o_dt == DT_F32)
         gemm_simt_kernel<float, float><<<grid, 256, 0, st>>>((const float*)A, W, bias, (const float*)res, (float*)out, T, K, N, taps, act);
@@ -175,6 +177,7 @@ __global__ void layernorm_kernel(const T* __restrict__ x, const T* __restrict__ 
 int launch_layernorm(const void* x, const void* res, const float* gamma, const float* beta, void* out,
                      DType dt, int64_t rows, int D, float eps, cudaStream_t st) {
     if (D > 1024) return fail(ASRB_E_ARG, "layernorm: D=%d > 1024", D);
+    ProfScope ps("layernorm", st, 0.0, (double)rows * D * (dt == DT_F32 ? 4.0 : 2.0) * (res ? 3.0 : 2.0));
     const unsigned grid = (unsigned)((rows + 7) / 8);
     if (dt == DT_F32)
         layernorm_kernel<float><<<grid, 256, 0, st>>>((const float*)x, (const float*)res, gamma, beta, (float*)out, rows, D, eps);
@@ -199,6 +202,7 @@ __global__ void glu_kernel(const T* __restrict__ x, T* __restrict__ out, int64_t
 
 int launch_glu(const void* x, void* out, DType dt, int64_t rows, int D, cudaStream_t st) {
     const int64_t total = rows * D;
+    ProfScope ps("glu", st, 0.0, (double)rows * D * (dt == DT_F32 ? 4.0 : 2.0) * 3.0);
     unsigned grid = (unsigned)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
     if (grid == 0) grid = 1;
     if (dt == DT_F32) glu_kernel<float><<<grid, 256, 0, st>>>((const float*)x, (float*)out, rows, D);
@@ -273,6 +277,8 @@ static int dwconv_dispatch(const void* x, const float* w, const float* bias, voi
 int launch_dwconv(const void* x, DType x_dt, const float* w, const float* bias, void* out, DType o_dt,
                   int64_t B, int64_t T, int D, int KW, Act act, const float* pos_scales, cudaStream_t st) {
     if (D & 1) return fail(ASRB_E_ARG, "dwconv: D=%d must be even", D);
+    ProfScope ps(KW == 15 ? "dwconv15_bn_silu" : (pos_scales ? "dwconv3_gelu_pos" : "dwconv3_gelu"), st, 2.0 * B * T * (double)D * KW,
+                 (double)B * T * D * ((x_dt == DT_F32 ? 4.0 : 2.0) + (o_dt == DT_F32 ? 4.0 : 2.0)));
     if (x_dt == DT_F32 && o_dt == DT_F32) return dwconv_dispatch<float, float>(x, w, bias, out, B, T, D, KW, act, pos_scales, st);
     if (x_dt == DT_BF16 && o_dt == DT_BF16) return dwconv_dispatch<__nv_bfloat16, __nv_bfloat16>(x, w, bias, out, B, T, D, KW, act, pos_scales, st);
     if (x_dt == DT_BF16 && o_dt == DT_F32) return dwconv_dispatch<__nv_bfloat16, float>(x, w, bias, out, B, T, D, KW, act, pos_scales, st);
@@ -365,6 +371,7 @@ static int attention_dispatch(const void* q, const void* k, const void* v, int64
 
 int launch_attention_simt_ex(const void* q, const void* k, const void* v, int64_t ldq, int64_t ldk, int64_t ldv,
                              void* out, DType dt, int64_t B, int64_t T, int D, int H, float scale, cudaStream_t st) {
+    ProfScope ps("attention_simt", st, 4.0 * B * (double)T * T * D, (double)B * T * D * 4.0 * (dt == DT_F32 ? 4.0 : 2.0));
     if (dt == DT_F32) return attention_dispatch<float>(q, k, v, ldq, ldk, ldv, out, B, T, D, H, scale, st);
     return attention_dispatch<__nv_bfloat16>(q, k, v, ldq, ldk, ldv, out, B, T, D, H, scale, st);
 }
@@ -391,6 +398,7 @@ __global__ void rmsnorm_kernel(const float* __restrict__ x, const float* __restr
 }
 
 int launch_rmsnorm(const float* x, const float* w, float* out, int64_t rows, int D, cudaStream_t st) {
+    ProfScope ps("rmsnorm", st, 0.0, (double)rows * D * 8.0);
     rmsnorm_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(x, w, out, rows, D, 1.1920928955078125e-07f);
     ASRB_LAUNCH_CHECK();
     return ASRB_OK;
@@ -430,6 +438,7 @@ __global__ void rotary_headnorm_kernel(float* __restrict__ x_all, int64_t ld, co
 int launch_rotary_headnorm(float* x, int64_t ld, const float* xa, const float* ln_w, const float* freqs,
                            int64_t B, int64_t T, int D, int H, float pre_scale, cudaStream_t st) {
     const int64_t warps = B * T * H;
+    ProfScope ps("rotary_headnorm", st, 0.0, (double)B * T * D * 12.0);
     rotary_headnorm_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(x, ld, xa, ln_w, freqs, B * T, T, D, H,
                                                                          pre_scale, 1.1920928955078125e-07f);
     ASRB_LAUNCH_CHECK();

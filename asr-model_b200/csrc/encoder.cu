@@ -345,6 +345,7 @@ int encoder_body(asrb_encoder* e, const EncBuffers& w, const float* x_c1, int in
         f1.B = B; f1.T = T; f1.K = D; f1.N = F; f1.taps = 1; f1.epilogue = TC_BIAS_ACT; f1.act = ACT_RELU;
         ASRB_TRY(launch_gemm_tc(f1, st));
         ASRB_TRY(tc_gemm_ln((const __nv_bfloat16*)w.ffn, e->wf2_h, e->bf2, (const __nv_bfloat16*)w.Y, e->n2g, e->n2b, fin, w.H, B, T, F, D, 1, st));
+        ProfScope ps("convert", st, 0.0, 6.0 * rows * D);
         if (!same) { convert_kernel<<<148 * 8, 256, 0, st>>>((const __nv_bfloat16*)fin, (float*)out, rows * D); ASRB_LAUNCH_CHECK(); }
     } else {
         ASRB_TRY(launch_gemm_simt(w.X, DT_F32, e->win_f, e->bin, nullptr, w.wide, DT_F32, B, T, D, 3 * D, 1, ACT_NONE, st));

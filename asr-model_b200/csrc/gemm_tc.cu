@@ -459,6 +459,9 @@ int launch_gemm_tc(const TcGemmArgs& a, cudaStream_t st) {
     p.m_tiles = (int)(a.B * p.tiles_per_utt);
     p.n_chunks = a.N / bn; p.n_out = n_out; p.eps = a.eps;
     const int units = a.epilogue == TC_LN ? p.m_tiles : p.m_tiles * p.n_chunks;
+    static const char* const tags[4] = {"gemm_tc_bias_act", "gemm_tc_glu", "gemm_tc_res_act", "gemm_tc_layernorm"};
+    ProfScope ps(tags[a.epilogue], st, 2.0 * a.B * a.T * (double)a.N * a.K * a.taps,
+                 2.0 * a.B * a.T * ((double)a.K + n_out + (a.res ? n_out : 0)) + 2.0 * a.N * a.K * a.taps);
 #define ASRB_TC(BN_, EPI_) return launch_one<BN_, EPI_>(ma, mw, mo, p, units, st)
     if (bn == 256) {
         switch (a.epilogue) {

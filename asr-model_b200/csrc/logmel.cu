@@ -305,6 +305,9 @@ int logmel_pass1(const asrb_logmel_plan* pl, const float* pcm, int64_t batch, in
     p.window = pl->d_window; p.twiddle = pl->d_twiddle; p.mel_lo = pl->d_lo; p.mel_cnt = pl->d_cnt;
     p.mel_w = pl->d_w; p.out = out; p.keys = keys;
     ASRB_CUDA(cudaMemsetAsync(keys, 0, sizeof(uint32_t) * batch, st));
+    const double frames = (double)batch * p.T;
+    ProfScope ps("logmel_stft_mel", st, frames * 2.5 * pl->n_fft * log2((double)pl->n_fft),
+                 4.0 * batch * ((double)n_samples + (double)pl->n_mels * p.T));
     if (pl->n_fft == 400) return launch_logmel<400, 20, 32>(pl, p, batch, st);
     return launch_logmel<1024, 32, 16>(pl, p, batch, st);
 }
@@ -332,6 +335,7 @@ extern "C" int asrb_logmel_f32(const asrb_logmel_plan* pl, const float* pcm, int
     const int64_t per = (int64_t)pl->n_mels * T;
     int gx = (int)((per + 256 * 8 - 1) / (256 * 8));
     if (gx < 1) gx = 1;
+    ProfScope ps("logmel_floor", st, 0.0, 0.0);
     logmel_floor_kernel<<<dim3(gx, (unsigned)batch), 256, 0, st>>>(out, keys, lengths, n_samples, pl->hop, pl->n_mels, T);
     ASRB_LAUNCH_CHECK();
     return ASRB_OK;

@@ -148,6 +148,17 @@ int asrb_attention_forward(asrb_attention* att, const float* x, int64_t batch, i
                            float* out, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * Measurement aid (process-wide; off by default, not for production): between
+ * asrb_profile_begin() and asrb_profile_end() every kernel launch of this library is
+ * bracketed by CUDA events on its stream.  asrb_profile_end() returns the record count;
+ * asrb_profile_get(i) yields the kernel tag, its device time and the ALGORITHMIC flops and
+ * HBM bytes of that launch (the roofline numerators of DESIGN.md).
+ * ---------------------------------------------------------------------------------- */
+int asrb_profile_begin(void);
+int asrb_profile_end(void);
+int asrb_profile_get(int index, const char** tag, float* ms, double* flops, double* bytes);
+
+/* ------------------------------------------------------------------------------------
  * Test hooks (exported so the GPU unit tests can check building blocks in isolation
  * through the same ABI; not needed by an integration).
  * ---------------------------------------------------------------------------------- */

@@ -1,0 +1,147 @@
+"""GPU parity of AudioEncoder (through the C ABI) against the CPU oracle / reference fixtures.
+fp32 variant: <= 1e-4 max-abs.  bf16 variant: allclose(atol=2e-2, rtol=1e-2) vs the fp32
+oracle (BASELINE.json north_star)."""
+import json
+import os
+
+import pytest
+import torch
+
+import oracle
+from asr_model_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ab(built_lib):
+    import asr_model_b200 as ab
+    return ab
+
+
+def _enc(ab, sd, mels, D, H, L, enc, compute, **kw):
+    m = ab.AudioEncoder(mels, D, H, L, "gelu", "AbbyNormal", norm=False, enc=enc, compute=compute, **kw).eval()
+    m.load_state_dict(sd)
+    return m
+
+
+@pytest.mark.parametrize("name", ["enc_small", "enc_small_tel", "enc_m128_default", "enc_conv2"])
+def test_fp32_variant_matches_reference_fixtures(ab, golden, name):
+    pinned = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "PINNED.json")))
+    mels, D, H, L, B, T, enc, perturb = pinned["cases"][name]["cfg"]
+    mm = 80 if mels == 1 else mels
+    sd = oracle.random_encoder_state_dict(mm, D, L, enc, seed=11, perturb=perturb)
+    x = torch.from_numpy(golden["encoder"][name + "_x"])
+    y = _enc(ab, sd, mm, D, H, L, enc, "fp32")(x.cuda()).cpu()
+    ref = torch.from_numpy(golden["encoder"][name + "_y"])
+    assert y.shape == ref.shape and y.dtype == torch.float32
+    assert float((y - ref).abs().max()) <= 1e-4
+
+
+@pytest.mark.parametrize("D,H,L,enc,T", [(128, 4, 2, False, 300), (256, 4, 2, True, 333), (512, 4, 4, False, 1001)])
+def test_fp32_variant_matches_oracle_on_logmel_input(ab, D, H, L, enc, T):
+    sd = oracle.random_encoder_state_dict(80, D, L, enc, seed=2, perturb=True)
+    waves = synth.make_batch("WH", (T - 1) * 160)
+    mel = oracle.log_mel_batch(waves, 80, 400)
+    ref = oracle.audio_encoder_forward(sd, mel, H)
+    y = _enc(ab, sd, 80, D, H, L, enc, "fp32")(mel.cuda()).cpu()
+    assert float((y - ref).abs().max()) <= 1e-4
+
+
+@pytest.mark.parametrize("D,H,L,enc,B,T,perturb", [
+    (128, 4, 2, False, 3, 300, True),
+    (128, 4, 2, True, 2, 257, True),
+    (256, 4, 1, True, 2, 130, True),
+    (384, 4, 1, False, 2, 200, True),
+    (512, 4, 4, False, 4, 1001, False),      # BASELINE config 1 shapes (4 x 10 s), default init
+    (512, 4, 4, True, 2, 1001, False),
+    (512, 4, 4, False, 2, 1001, True),
+])
+def test_bf16_variant_within_tolerance(ab, D, H, L, enc, B, T, perturb):
+    sd = oracle.random_encoder_state_dict(80, D, L, enc, seed=3, perturb=perturb)
+    waves = synth.make_batch("WHT2"[:B] if B <= 4 else "W" * B, (T - 1) * 160)
+    mel = oracle.log_mel_batch(waves, 80, 400)
+    ref = oracle.audio_encoder_forward(sd, mel, H)
+    y = _enc(ab, sd, 80, D, H, L, enc, "bf16")(mel.cuda())
+    assert y.dtype == torch.bfloat16 and y.shape == ref.shape
+    err = (y.float().cpu() - ref).abs()
+    print(f"bf16 D={D} enc={enc}: max-abs {float(err.max()):.4f}  max-abs/absmax {float(err.max() / ref.abs().max()):.5f}")
+    assert bool((err <= 2e-2 + 1e-2 * ref.abs()).all()), float(err.max())
+
+
+def test_bf16_wide_model_runs_unfused_layernorm(ab):
+    """D=1024 (BASELINE config 4 width): LayerNorm rows do not fit TMEM, unfused path."""
+    sd = oracle.random_encoder_state_dict(80, 1024, 1, True, seed=4, perturb=False)
+    waves = synth.make_batch("WH", 200 * 160)
+    mel = oracle.log_mel_batch(waves, 80, 400)
+    ref = oracle.audio_encoder_forward(sd, mel, 16)
+    y = _enc(ab, sd, 80, 1024, 16, 1, True, "bf16")(mel.cuda()).float().cpu()
+    err = (y - ref).abs()
+    assert bool((err <= 4e-2 + 2e-2 * ref.abs()).all()), float(err.max())   # one extra bf16 rounding
+
+
+def test_conv2_single_channel_stream_bf16(ab):
+    sd = oracle.random_encoder_state_dict(80, 128, 1, False, seed=5, perturb=True)
+    x = torch.randn(2, 1, 150, generator=torch.Generator().manual_seed(1))
+    ref = oracle.audio_encoder_forward(sd, x, 4)
+    y = _enc(ab, sd, 80, 128, 4, 1, False, "bf16")(x.cuda()).float().cpu()
+    assert bool(((y - ref).abs() <= 2e-2 + 1e-2 * ref.abs()).all())
+
+
+@pytest.mark.parametrize("compute", ["fp32", "bf16"])
+def test_fused_pcm_to_hidden_equals_two_calls(ab, compute):
+    from asr_model_b200.frontend import LogMel
+    sd = oracle.random_encoder_state_dict(80, 128, 2, True, seed=6, perturb=True)
+    waves = synth.make_batch("WHTZ", 16000).cuda()
+    m = _enc(ab, sd, 80, 128, 4, 2, True, compute)
+    fe = LogMel(80, 400)
+    h, mel = m.forward_pcm(waves, fe, return_logmel=True)
+    mel2 = fe(waves)
+    assert torch.equal(mel, mel2)
+    h2 = m(mel2)
+    assert torch.equal(h, h2)
+    h3 = m.forward_pcm(waves, fe)                        # without materialising the feature tensor
+    assert torch.equal(h, h3)
+    lengths = torch.tensor([16000, 8000, 4810, 0])
+    hr = m.forward_pcm(waves, fe, lengths=lengths)
+    assert torch.equal(hr, m(fe(waves, lengths)))
+
+
+def test_dict_input_and_2d_input(ab):
+    sd = oracle.random_encoder_state_dict(80, 128, 1, False, seed=7, perturb=True)
+    m = _enc(ab, sd, 80, 128, 4, 1, False, "fp32")
+    x = torch.randn(80, 40).cuda()
+    y = m(x)
+    assert y.shape == (1, 40, 128)
+    d = m({"a": x, "b": torch.randn(1, 1, 40).cuda(), "c": None})
+    assert set(d) == {"a", "b"} and torch.equal(d["a"], y)
+
+
+def test_weight_update_invalidates_the_packed_copy(ab):
+    sd = oracle.random_encoder_state_dict(80, 128, 1, False, seed=8, perturb=True)
+    m = _enc(ab, sd, 80, 128, 4, 1, False, "fp32")
+    x = torch.randn(1, 80, 64).cuda()
+    y0 = m(x).clone()
+    with torch.no_grad():
+        m.conv1[0].bias.add_(1.0)
+    assert not torch.equal(m(x), y0)
+    m.load_state_dict(sd)
+    assert torch.equal(m(x), y0)
+    m.train()
+    with pytest.raises(Exception):
+        m(x)
+
+
+def test_attention_rotary_block_matches_reference_fixture(ab, golden):
+    sd = oracle.random_attention_state_dict(64, 4, seed=3)
+    a = ab.AudioAttention(64, 4)
+    a.load_state_dict(sd)
+    x = torch.from_numpy(golden["attention"]["att_x"])
+    y = a(x.cuda()).cpu()
+    assert float((y - torch.from_numpy(golden["attention"]["att_y"])).abs().max()) <= 1e-4
+    # longer sequence against the oracle (B=1 semantics per utterance)
+    sd = oracle.random_attention_state_dict(256, 4, seed=4)
+    a = ab.AudioAttention(256, 4)
+    a.load_state_dict(sd)
+    x = torch.randn(2, 301, 256, generator=torch.Generator().manual_seed(2))
+    assert float((a(x.cuda()).cpu() - oracle.attention_forward(sd, x, 4)).abs().max()) <= 2e-4

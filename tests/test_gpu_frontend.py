@@ -1,0 +1,110 @@
+"""GPU parity of the fused log-mel kernel (through the C ABI) against the CPU oracle and the
+reference fixtures.  Tolerance: 1e-4 max-abs in fp32 (BASELINE.json north_star)."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from asr_model_b200 import synth
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def ab(built_lib):
+    import asr_model_b200 as ab
+    assert torch.cuda.is_available()
+    return ab
+
+
+@pytest.mark.parametrize("n_mels,n_fft", [(80, 400), (128, 400), (80, 1024), (128, 1024)])
+def test_mixed_signal_classes_match_oracle(ab, n_mels, n_fft):
+    waves = synth.make_batch("WHTZ2WH", 16000 + 37)            # ragged tail, all classes in one batch
+    ref = oracle.log_mel_batch(waves, n_mels, n_fft)
+    out = ab.log_mel(waves.cuda(), n_mels, n_fft).cpu()
+    assert out.shape == ref.shape
+    assert float((out - ref).abs().max()) <= TOL
+    ref64 = oracle.log_mel_batch(waves, n_mels, n_fft, dtype=torch.float64)
+    assert float((out.double() - ref64).abs().max()) <= TOL
+    assert torch.all(out[3] == -1.5)                          # class Z: exactly -1.5
+
+
+def test_reference_fixtures(ab, golden):
+    n = 0
+    for key in golden["frontend"].files:
+        if not key.startswith("logmel_"):
+            continue
+        _, m, f, kind, length = key.split("_")
+        ref = torch.from_numpy(golden["frontend"][key])
+        out = ab.log_mel(synth.make_wave(kind, int(length)).cuda(), int(m[1:]), int(f[1:])).cpu()
+        assert out.shape == ref.shape, key
+        assert float((out - ref).abs().max()) <= TOL, key
+        n += 1
+    assert n == 20
+
+
+@pytest.mark.parametrize("n_fft", [400, 1024])
+def test_ragged_lengths_pad_with_zero_and_use_own_max(ab, n_fft):
+    waves = synth.make_batch("WHT", 12000)
+    lengths = [12000, 4810, 0]
+    ref = oracle.log_mel_batch(waves, 80, n_fft, lengths=lengths)
+    out = ab.log_mel(waves.cuda(), 80, n_fft, lengths=torch.tensor(lengths)).cpu()
+    assert float((out - ref).abs().max()) <= TOL
+    assert torch.all(out[1, :, 1 + 4810 // 160:] == 0.0)
+    assert torch.all(out[2, :, 1:] == 0.0) and torch.all(out[2, :, 0] == -1.5)
+
+
+def test_edge_shapes(ab):
+    for n in (0, 1, 159, 160, 161, 399, 400, 5000):
+        w = synth.make_wave("W", max(n, 1))[:n]
+        ref = oracle.log_mel_utterance(w, 80, 400) if n > 0 else torch.full((80, 1), -1.5)
+        out = ab.log_mel(w.cuda(), 80, 400).cpu()
+        assert out.shape == (80, 1 + n // 160)
+        assert float((out - ref).abs().max()) <= TOL, n
+    assert ab.log_mel(torch.zeros(0, 1600, device="cuda"), 80, 400).shape == (0, 80, 11)
+
+
+def test_unaligned_rows_take_the_scalar_path(ab):
+    base = synth.make_batch("WH", 8003)
+    dev = base.cuda()
+    view = dev[:, 1:8002]                                       # stride 8003, offset 1: no 16-B alignment
+    assert not view.is_contiguous()
+    ref = oracle.log_mel_batch(base[:, 1:8002].contiguous(), 80, 400)
+    from asr_model_b200.frontend import LogMel
+    out = LogMel(80, 400)(view).cpu()
+    assert float((out - ref).abs().max()) <= TOL
+
+
+def test_full_size_30s_clips(ab):
+    """BASELINE config sizes: 30 s clips. Oracle on 3 of them + size-independent properties."""
+    N = 480000
+    waves = torch.cat([synth.make_batch("WHT", N), torch.zeros(1, N)])
+    out = ab.log_mel(waves.cuda(), 80, 400)
+    assert out.shape == (4, 80, 3001)
+    ref = oracle.log_mel_batch(waves[:3], 80, 400)
+    assert float((out[:3].cpu() - ref).abs().max()) <= TOL
+    assert torch.all(out[3] == -1.5)
+    # dynamic range: max - min <= 2.0 (8 in log10 / 4) per utterance
+    flat = out.flatten(1)
+    assert torch.all(flat.max(1).values - flat.min(1).values <= 2.0 + 1e-6)
+    # batch independence: an utterance alone == the same utterance inside a batch
+    alone = ab.log_mel(waves[1:2].cuda(), 80, 400)
+    assert torch.equal(alone[0], out[1])
+    # time-shift covariance: shifting by k hops shifts interior frames
+    w = waves[0].cuda()
+    a = ab.log_mel(w[:160000], 80, 400)
+    bshift = ab.log_mel(w[1600:161600], 80, 400)
+    inner = (a[:, 20:900] - bshift[:, 10:890]).abs().max()
+    assert float(inner) <= 2e-4
+
+
+def test_extract_features_drop_in(ab):
+    class Tok:
+        def encode(self, s):
+            return [5, 6]
+    w = synth.make_wave("H", 16000)
+    r = ab.extract_features({"audio": {"array": w.numpy(), "sampling_rate": 16000}, "transcription": "x"},
+                            Tok(), spectrogram=True, mels=128)
+    assert r["labels"] == [5, 6] and r["spectrogram"].shape == (128, 101) and r["spectrogram"].is_cuda
+    assert float((r["spectrogram"].cpu() - oracle.log_mel_utterance(w, 128, 1024)).abs().max()) <= TOL

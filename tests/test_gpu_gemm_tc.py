@@ -1,0 +1,76 @@
+"""The tcgen05/TMEM/TMA implicit-GEMM kernel in isolation (asrb_test_gemm_tc) against a plain
+PyTorch fp32 reference of the same op on the same bf16-rounded operands."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref(a, w, bias, res, gamma, beta, taps, epi, act, N):
+    B, T, K = a.shape
+    af = a.float()
+    wf = w.float().view(N, taps, K)
+    acc = torch.zeros(B, T, N, device=a.device)
+    for tap in range(taps):
+        sh = tap - taps // 2
+        src = torch.zeros_like(af)
+        if sh < 0:
+            src[:, -sh:] = af[:, :T + sh]
+        elif sh > 0:
+            src[:, :T - sh] = af[:, sh:]
+        else:
+            src = af
+        acc += src @ wf[:, tap].t()
+    acc = acc + bias
+    if epi == 1:                                    # GLU with [128 value | 128 gate] per 256 rows
+        v = acc.view(B, T, N // 256, 2, 128)
+        return (v[..., 0, :] * torch.sigmoid(v[..., 1, :])).reshape(B, T, N // 2)
+    if res is not None:
+        acc = acc + res.float()
+    if epi == 3:
+        return F.layer_norm(acc, (N,), gamma, beta, 1e-5)
+    return {0: lambda x: x, 1: F.gelu, 2: F.relu, 3: F.silu, 4: lambda x: F.gelu(F.gelu(x))}[act](acc)
+
+
+CASES = [
+    # B, T, K, N, taps, epi, act
+    (1, 128, 64, 128, 1, 0, 0),
+    (1, 256, 128, 256, 1, 0, 0),
+    (1, 300, 512, 512, 1, 0, 1),
+    (2, 1001, 512, 1536, 1, 0, 0),
+    (3, 200, 128, 128, 3, 0, 1),        # k3 conv: halo must not leak across utterances
+    (2, 333, 512, 512, 3, 3, 0),        # k3 conv + LayerNorm (2 chunks of 256)
+    (1, 129, 128, 128, 1, 3, 0),        # LN, one 128 chunk, double-buffered accumulators
+    (2, 260, 256, 384, 1, 3, 0),        # LN over 3 chunks of 128
+    (2, 260, 256, 256, 1, 3, 0),
+    (2, 500, 512, 1024, 1, 1, 0),       # GLU
+    (2, 500, 512, 512, 1, 2, 1),        # residual + GELU
+    (1, 4000, 2048, 512, 1, 3, 0),      # FFN2 + residual + LN
+    (1, 777, 512, 2048, 1, 0, 2),       # FFN1 + ReLU
+    (40, 130, 256, 256, 3, 0, 4),       # many small utterances, persistent loop wraps
+]
+
+
+@pytest.mark.parametrize("B,T,K,N,taps,epi,act", CASES)
+def test_gemm_tc_matches_torch(built_lib, B, T, K, N, taps, epi, act):
+    lib = built_lib.load()
+    g = torch.Generator(device="cuda").manual_seed(B * 1000 + T + K + N + taps + epi)
+    a = (torch.randn(B, T, K, device="cuda", generator=g) * 0.5).bfloat16()
+    w = (torch.randn(N, taps * K, device="cuda", generator=g) / (taps * K) ** 0.5).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g) * 0.1
+    n_out = N // 2 if epi == 1 else N
+    res = (torch.randn(B, T, n_out, device="cuda", generator=g)).bfloat16() if epi in (2, 3) and (T % 2 == 0 or epi == 2) else None
+    gamma = 1 + 0.2 * torch.randn(N, device="cuda", generator=g)
+    beta = 0.1 * torch.randn(N, device="cuda", generator=g)
+    out = torch.full((B, T, n_out), float("nan"), device="cuda", dtype=torch.bfloat16)
+    rc = lib.asrb_test_gemm_tc(a.data_ptr(), w.data_ptr(), bias.data_ptr(), res.data_ptr() if res is not None else None,
+                               gamma.data_ptr(), beta.data_ptr(), out.data_ptr(), B, T, K, N, taps, epi, act, None)
+    built_lib.check(rc, "asrb_test_gemm_tc")
+    torch.cuda.synchronize()
+    ref = _ref(a, w, bias, res, gamma, beta, taps, epi, act, N)
+    assert not torch.isnan(out.float()).any(), "rows were left unwritten"
+    err = (out.float() - ref).abs()
+    tol = 2e-2 + 1e-2 * ref.abs()                      # bf16 store rounding dominates
+    assert bool((err <= tol).all()), f"max err {float(err.max())} at {int(err.argmax())}"
+    assert float(err.mean()) < 3e-3
