@@ -225,64 +225,122 @@ template <> struct pair_io<__nv_bfloat16> {
     __device__ static void st(__nv_bfloat16* p, float2 v) { *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(v.x, v.y); }
 };
 
-template <class TI, class TO, int KW, int TT>
-__global__ void __launch_bounds__(128)
+template <bool FAST> __device__ __forceinline__ float dw_act(float v, int act) {
+    if (FAST) {
+        switch (act) {
+            case ACT_GELU: return gelu_fast(v);
+            case ACT_SILU: return v * sigmoid_fast(v);
+            case ACT_GELU_GELU: return gelu_fast(gelu_fast(v));
+            case ACT_RELU: return fmaxf(v, 0.f);
+            default: return v;
+        }
+    }
+    return apply_act(v, act);
+}
+
+// Block = 128 time steps x 64 channels of one utterance: the input tile (+ halo) is staged in
+// shared memory with 16-byte loads, then every thread slides a KW-wide register window down
+// 16 time steps of one channel pair (1 LDS.64 per output pair), storing channel-contiguous rows.
+template <class TI, class TO, int KW, bool FAST>
+__global__ void __launch_bounds__(256)
 dwconv_kernel(const TI* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
-              TO* __restrict__ out, int64_t T, int D, int act, const float* __restrict__ pos_scales) {
-    const int c = (blockIdx.x * 128 + threadIdx.x) * 2;
-    if (c >= D) return;
+              TO* __restrict__ out, int64_t T, int D, int act, const float* __restrict__ pos, float* __restrict__ out32) {
+    constexpr int TB = 128, CB = 64, TL = 16, HALO = KW / 2, ROWS = TB + KW - 1;
+    __shared__ __align__(16) float tile[ROWS][CB];
     const int b = blockIdx.z;
-    const int64_t t0 = (int64_t)blockIdx.y * TT;
+    const int64_t t0 = (int64_t)blockIdx.y * TB;
+    const int c0 = blockIdx.x * CB;
+    const TI* xb = x + (int64_t)b * T * D + c0;
+    constexpr int VEC = 16 / sizeof(TI);                        // elements per 16-byte load
+    for (int i = threadIdx.x; i < ROWS * (CB / VEC); i += 256) {
+        const int rr = i / (CB / VEC), cv = (i - rr * (CB / VEC)) * VEC;
+        const int64_t t = t0 - HALO + rr;
+        float vals[VEC];
+        if (t >= 0 && t < T) {
+            const uint4 q = __ldg(reinterpret_cast<const uint4*>(xb + t * D + cv));
+            if (sizeof(TI) == 4) {
+                const float* f = reinterpret_cast<const float*>(&q);
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) vals[j] = f[j];
+            } else {
+                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+                for (int j = 0; j < VEC / 2; ++j) { const float2 f = __bfloat1622float2(h[j]); vals[2 * j] = f.x; vals[2 * j + 1] = f.y; }
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) vals[j] = 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < VEC; j += 4) *reinterpret_cast<float4*>(&tile[rr][cv + j]) = make_float4(vals[j], vals[j + 1], vals[j + 2], vals[j + 3]);
+    }
+    __syncthreads();
+    const int cp = (threadIdx.x & 31) * 2;                      // channel pair inside the block
+    const int ts = (threadIdx.x >> 5) * TL;                     // first time step of this warp's slice
+    const int c = c0 + cp;
     float2 wv[KW];
 #pragma unroll
-    for (int j = 0; j < KW; ++j) wv[j] = *reinterpret_cast<const float2*>(w + (int64_t)j * D + c);
-    const float2 bv = *reinterpret_cast<const float2*>(bias + c);
-    float2 xv[TT + KW - 1];
-    const TI* xb = x + (int64_t)b * T * D + c;
+    for (int j = 0; j < KW; ++j) wv[j] = __ldg(reinterpret_cast<const float2*>(w + (int64_t)j * D + c));
+    const float2 bv = __ldg(reinterpret_cast<const float2*>(bias + c));
+    float2 win[KW];
 #pragma unroll
-    for (int i = 0; i < TT + KW - 1; ++i) {
-        const int64_t t = t0 - KW / 2 + i;
-        xv[i] = (t >= 0 && t < T) ? pair_io<TI>::ld(xb + t * D) : make_float2(0.f, 0.f);
-    }
-    const int half = D / 2;
+    for (int j = 0; j < KW - 1; ++j) win[j + 1] = *reinterpret_cast<const float2*>(&tile[ts + j][cp]);
 #pragma unroll
-    for (int o = 0; o < TT; ++o) {
-        const int64_t t = t0 + o;
-        if (t >= T) break;
-        float2 a = bv;
+    for (int o = 0; o < TL; ++o) {
 #pragma unroll
-        for (int j = 0; j < KW; ++j) { a.x = fmaf(wv[j].x, xv[o + j].x, a.x); a.y = fmaf(wv[j].y, xv[o + j].y, a.y); }
-        a.x = apply_act(a.x, act); a.y = apply_act(a.y, act);
-        if (pos_scales) {                                   // + sinusoids(T, D)[t, c] (essentials.py:354-358)
-            const float tf = (float)t;
-            a.x += c < half ? sinf(tf * pos_scales[c]) : cosf(tf * pos_scales[c - half]);
-            a.y += (c + 1) < half ? sinf(tf * pos_scales[c + 1]) : cosf(tf * pos_scales[c + 1 - half]);
+        for (int j = 0; j < KW - 1; ++j) win[j] = win[j + 1];
+        win[KW - 1] = *reinterpret_cast<const float2*>(&tile[ts + o + KW - 1][cp]);
+        const int64_t t = t0 + ts + o;
+        if (t < T) {
+            float2 a = bv;
+#pragma unroll
+            for (int j = 0; j < KW; ++j) { a.x = fmaf(wv[j].x, win[j].x, a.x); a.y = fmaf(wv[j].y, win[j].y, a.y); }
+            a.x = dw_act<FAST>(a.x, act); a.y = dw_act<FAST>(a.y, act);
+            if (pos) { const float2 pv = __ldg(reinterpret_cast<const float2*>(pos + t * D + c)); a.x += pv.x; a.y += pv.y; }
+            pair_io<TO>::st(out + ((int64_t)b * T + t) * D + c, a);
+            if (out32) *reinterpret_cast<float2*>(out32 + ((int64_t)b * T + t) * D + c) = a;
         }
-        pair_io<TO>::st(out + ((int64_t)b * T + t) * D + c, a);
     }
+}
+
+// sinusoids(T, D) (essentials.py:354-358) from the host-built scale table: [T][D] fp32
+__global__ void pos_table_kernel(float* __restrict__ pos, const float* __restrict__ scales, int64_t T, int D) {
+    const int half = D / 2;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < T * D; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t t = i / D; const int c = (int)(i - t * D);
+        const float tf = (float)t;
+        pos[i] = c < half ? sinf(tf * scales[c]) : cosf(tf * scales[c - half]);
+    }
+}
+int launch_pos_table(float* pos, const float* scales, int64_t T, int D, cudaStream_t st) {
+    ProfScope ps("pos_table", st, 0.0, 4.0 * T * D);
+    pos_table_kernel<<<(unsigned)((T * D + 255) / 256 < 2048 ? (T * D + 255) / 256 : 2048), 256, 0, st>>>(pos, scales, T, D);
+    ASRB_LAUNCH_CHECK();
+    return ASRB_OK;
 }
 
 template <class TI, class TO>
 static int dwconv_dispatch(const void* x, const float* w, const float* bias, void* out, int64_t B, int64_t T,
-                           int D, int KW, int act, const float* pos, cudaStream_t st) {
-    constexpr int TT = 16;
-    dim3 grid((unsigned)((D / 2 + 127) / 128), (unsigned)((T + TT - 1) / TT), (unsigned)B);
-    if (KW == 15) dwconv_kernel<TI, TO, 15, TT><<<grid, 128, 0, st>>>((const TI*)x, w, bias, (TO*)out, T, D, act, pos);
-    else if (KW == 3) dwconv_kernel<TI, TO, 3, TT><<<grid, 128, 0, st>>>((const TI*)x, w, bias, (TO*)out, T, D, act, pos);
+                           int D, int KW, int act, const float* pos, bool fast, cudaStream_t st, float* out32) {
+    dim3 grid((unsigned)(D / 64), (unsigned)((T + 127) / 128), (unsigned)B);
+#define ASRB_DW(KW_, F_) dwconv_kernel<TI, TO, KW_, F_><<<grid, 256, 0, st>>>((const TI*)x, w, bias, (TO*)out, T, D, act, pos, out32)
+    if (KW == 15) { if (fast) ASRB_DW(15, true); else ASRB_DW(15, false); }
+    else if (KW == 3) { if (fast) ASRB_DW(3, true); else ASRB_DW(3, false); }
     else return fail(ASRB_E_ARG, "dwconv: kernel width %d unsupported", KW);
+#undef ASRB_DW
     ASRB_LAUNCH_CHECK();
     return ASRB_OK;
 }
 
 int launch_dwconv(const void* x, DType x_dt, const float* w, const float* bias, void* out, DType o_dt,
-                  int64_t B, int64_t T, int D, int KW, Act act, const float* pos_scales, cudaStream_t st) {
-    if (D & 1) return fail(ASRB_E_ARG, "dwconv: D=%d must be even", D);
-    ProfScope ps(KW == 15 ? "dwconv15_bn_silu" : (pos_scales ? "dwconv3_gelu_pos" : "dwconv3_gelu"), st, 2.0 * B * T * (double)D * KW,
+                  int64_t B, int64_t T, int D, int KW, Act act, const float* pos, bool fast, cudaStream_t st, float* out32) {
+    if (D % 64) return fail(ASRB_E_ARG, "dwconv: D=%d must be a multiple of 64", D);
+    ProfScope ps(KW == 15 ? "dwconv15_bn_silu" : (pos ? "dwconv3_gelu_pos" : "dwconv3_gelu"), st, 2.0 * B * T * (double)D * KW,
                  (double)B * T * D * ((x_dt == DT_F32 ? 4.0 : 2.0) + (o_dt == DT_F32 ? 4.0 : 2.0)));
-    if (x_dt == DT_F32 && o_dt == DT_F32) return dwconv_dispatch<float, float>(x, w, bias, out, B, T, D, KW, act, pos_scales, st);
-    if (x_dt == DT_BF16 && o_dt == DT_BF16) return dwconv_dispatch<__nv_bfloat16, __nv_bfloat16>(x, w, bias, out, B, T, D, KW, act, pos_scales, st);
-    if (x_dt == DT_BF16 && o_dt == DT_F32) return dwconv_dispatch<__nv_bfloat16, float>(x, w, bias, out, B, T, D, KW, act, pos_scales, st);
-    return dwconv_dispatch<float, __nv_bfloat16>(x, w, bias, out, B, T, D, KW, act, pos_scales, st);
+    if (x_dt == DT_F32 && o_dt == DT_F32) return dwconv_dispatch<float, float>(x, w, bias, out, B, T, D, KW, act, pos, fast, st, out32);
+    if (x_dt == DT_BF16 && o_dt == DT_BF16) return dwconv_dispatch<__nv_bfloat16, __nv_bfloat16>(x, w, bias, out, B, T, D, KW, act, pos, fast, st, out32);
+    if (x_dt == DT_BF16 && o_dt == DT_F32) return dwconv_dispatch<__nv_bfloat16, float>(x, w, bias, out, B, T, D, KW, act, pos, fast, st, out32);
+    return dwconv_dispatch<float, __nv_bfloat16>(x, w, bias, out, B, T, D, KW, act, pos, fast, st, out32);
 }
 
 // ------------------------------------------------------------------------------------------

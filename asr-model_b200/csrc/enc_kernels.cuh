@@ -31,10 +31,12 @@ int launch_layernorm(const void* x, const void* res, const float* gamma, const f
 int launch_glu(const void* x, void* out, DType dt, int64_t rows, int D, cudaStream_t st);
 
 // Depthwise conv along T, channels-last: out[b,t,c] = act(sum_j w[j][c] x[b,t+j-KW/2,c] + bias[c]);
-// pos_scales != NULL ([D/2] table s_j) adds sinusoids(t, c) (essentials.py:354-358) after the
-// activation; out may be a different storage type than x (the encoder's final store).
+// pos != NULL ([T][D] table from launch_pos_table) adds sinusoids(t, c) after the activation;
+// fast = approximate erf/exp (bf16 path); out may be a different storage type than x.  D % 64 == 0.
 int launch_dwconv(const void* x, DType x_dt, const float* w, const float* bias, void* out, DType o_dt,
-                  int64_t B, int64_t T, int D, int KW, Act act, const float* pos_scales, cudaStream_t st);
+                  int64_t B, int64_t T, int D, int KW, Act act, const float* pos, bool fast, cudaStream_t st,
+                  float* out32 = nullptr);     // optional fp32 copy of the output
+int launch_pos_table(float* pos, const float* scales, int64_t T, int D, cudaStream_t st);
 
 // Softmax attention, no mask: qkv [B][T][3D] (q | k | v, heads contiguous inside each) ->
 // out [B][T][D].  fp32 math on CUDA cores (the fp32 variant and small shapes).
@@ -59,12 +61,15 @@ struct TcGemmArgs {
     const __nv_bfloat16* W;      // [N][taps*K] tap-major (GLU: value/gate interleaved per tile)
     const float* bias;           // [N]
     const __nv_bfloat16* res;    // [B][T][Nout] or NULL
+    const float* res32;          // TC_LN: fp32 residual instead of res (post-norm residual streams stay fp32)
+    float* out32;                // TC_LN: optional fp32 copy of the output
     const float* gamma;          // TC_LN
     const float* beta;           // TC_LN
-    void* out;                   // [B][T][Nout] bf16
+    void* out;                   // [B][T][Nout] bf16 (fp32 when out_f32)
     int64_t B, T;
     int K, N, taps;
     int epilogue; int act; float eps;
+    int out_f32;                 // store fp32 (consumer is a depthwise conv, not an MMA); not with TC_LN
 };
 bool tc_gemm_supported(int K, int N, int epilogue);
 int  tc_glu_tile_n(int N);                    // BN the GLU weight interleave must use

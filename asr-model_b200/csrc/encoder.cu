@@ -90,7 +90,7 @@ extern "C" int asrb_encoder_create(const asrb_encoder_config* cfg, int n_tensors
     if (!cfg || !out || (n_tensors > 0 && (!names || !host_data || !numels)))
         return fail(ASRB_E_ARG, "asrb_encoder_create: NULL argument");
     const int D = cfg->dims, M = cfg->mels, L = cfg->layer, F = cfg->ffn;
-    if (D <= 0 || M <= 0 || L < 1 || (D & 1)) return fail(ASRB_E_ARG, "asrb_encoder_create: bad dims=%d mels=%d layer=%d", D, M, L);
+    if (D <= 0 || M <= 0 || L < 1 || (D % 64)) return fail(ASRB_E_ARG, "asrb_encoder_create: bad dims=%d (multiple of 64) mels=%d layer=%d (>= 1)", D, M, L);
     if (cfg->compute != ASRB_F32 && cfg->compute != ASRB_BF16) return fail(ASRB_E_ARG, "asrb_encoder_create: compute=%d", cfg->compute);
     if (D > 1024) return fail(ASRB_E_ARG, "asrb_encoder_create: dims=%d > 1024 unsupported", D);
     if (cfg->enc && (cfg->head <= 0 || D % cfg->head != 0 || F <= 0))
@@ -218,7 +218,7 @@ extern "C" void asrb_encoder_destroy(asrb_encoder* e) {
 namespace {
 
 struct EncBuffers {                    // carved from the caller's workspace
-    void* a0; void* X; void* Y; void* G; void* U; void* H; void* wide; void* ffn;
+    void* a0; void* X; void* Y; void* G; void* U; void* H; void* wide; void* ffn; float* pos;
     bool ok;
 };
 
@@ -229,10 +229,12 @@ size_t enc_ws_bytes(const asrb_encoder* e, int64_t B, int64_t T) {
     size_t n = 0;
     auto add = [&](size_t bytes) { n = align_up(n, 256) + bytes; };
     add(rows * (e->cfg.compute == ASRB_BF16 ? e->CP : e->cfg.mels) * es);   // a0
-    for (int i = 0; i < 5; ++i) add(rows * D * es);                         // X Y G U H
+    add(rows * D * es); add(rows * D * es);                                 // X Y
+    add(rows * D * 4); add(rows * D * es); add(rows * D * 4);               // G (fp32) U H (fp32): G, H feed depthwise convs
     const size_t wide = e->cfg.enc ? 3 * D : (e->cfg.compute == ASRB_F32 ? 2 * D : 0);
     add(rows * wide * es);                                                  // qkv | fp32 GLU input
     add(e->cfg.enc ? rows * e->cfg.ffn * es : 0);                           // FFN hidden
+    add((size_t)T * D * 4);                                                 // sinusoid table
     return align_up(n, 256) + 256;
 }
 
@@ -242,11 +244,12 @@ EncBuffers carve(const asrb_encoder* e, int64_t B, int64_t T, void* ws, size_t w
     Arena a(ws, ws_bytes);
     EncBuffers b;
     b.a0 = a.take<char>(rows * (e->cfg.compute == ASRB_BF16 ? e->CP : e->cfg.mels) * es);
-    b.X = a.take<char>(rows * D * es); b.Y = a.take<char>(rows * D * es); b.G = a.take<char>(rows * D * es);
-    b.U = a.take<char>(rows * D * es); b.H = a.take<char>(rows * D * es);
+    b.X = a.take<char>(rows * D * es); b.Y = a.take<char>(rows * D * es); b.G = a.take<char>(rows * D * 4);
+    b.U = a.take<char>(rows * D * es); b.H = a.take<char>(rows * D * 4);
     const size_t wide = e->cfg.enc ? 3 * D : (e->cfg.compute == ASRB_F32 ? 2 * D : 0);
     b.wide = a.take<char>(rows * wide * es);
     b.ffn = a.take<char>(e->cfg.enc ? rows * e->cfg.ffn * es : 0);
+    b.pos = a.take<float>((size_t)T * D);
     b.ok = a.ok();
     return b;
 }
@@ -264,11 +267,14 @@ __global__ void convert_kernel(const __nv_bfloat16* __restrict__ in, float* __re
 // GEMM(+residual) to bf16 followed by the row kernel.
 int tc_gemm_ln(const __nv_bfloat16* A, const __nv_bfloat16* W, const float* bias, const __nv_bfloat16* res,
                const float* gamma, const float* beta, void* out, void* tmp, int64_t B, int64_t T, int K, int N,
-               int taps, cudaStream_t st) {
+               int taps, cudaStream_t st, const float* res32 = nullptr, float* out32 = nullptr) {
     TcGemmArgs g{};
     g.A = A; g.W = W; g.bias = bias; g.res = res; g.gamma = gamma; g.beta = beta;
     g.B = B; g.T = T; g.K = K; g.N = N; g.taps = taps; g.act = ACT_NONE; g.eps = 1e-5f;
-    if (tc_gemm_supported(K, N, TC_LN)) { g.epilogue = TC_LN; g.out = out; return launch_gemm_tc(g, st); }
+    if (tc_gemm_supported(K, N, TC_LN)) {
+        g.epilogue = TC_LN; g.out = out; g.res32 = res32; g.out32 = out32;
+        return launch_gemm_tc(g, st);
+    }
     g.epilogue = res ? TC_RES_ACT : TC_BIAS_ACT; g.out = tmp;
     ASRB_TRY(launch_gemm_tc(g, st));
     return launch_layernorm(tmp, nullptr, gamma, beta, out, DT_BF16, B * T, N, 1e-5f, st);
@@ -296,6 +302,8 @@ int encoder_body(asrb_encoder* e, const EncBuffers& w, const float* x_c1, int in
         ASRB_TRY(launch_gemm_simt(w.a0, DT_F32, e->stem1_f, e->stem1_b, nullptr, w.X, DT_F32, B, T, e->cfg.mels, D, 3, stem_act, st));
     }
 
+    ASRB_TRY(launch_pos_table(w.pos, e->pos_scales, T, D, st));
+
     // ---- conv blocks (model.py:142-147) ----
     const bool direct_out = !e->cfg.enc;              // the last depthwise kernel stores the result itself
     for (int i = 0; i < L; ++i) {
@@ -305,26 +313,28 @@ int encoder_body(asrb_encoder* e, const EncBuffers& w, const float* x_c1, int in
             ASRB_TRY(tc_gemm_ln((const __nv_bfloat16*)w.X, lw.wc_h, lw.bc, nullptr, lw.gamma, lw.beta, w.Y, w.H, B, T, D, D, 3, st));
             TcGemmArgs g{};
             g.A = (const __nv_bfloat16*)w.Y; g.W = lw.w1_h; g.bias = lw.b1_glu; g.out = w.G;
-            g.B = B; g.T = T; g.K = D; g.N = 2 * D; g.taps = 1; g.epilogue = TC_GLU; g.act = ACT_NONE;
+            g.B = B; g.T = T; g.K = D; g.N = 2 * D; g.taps = 1; g.epilogue = TC_GLU; g.act = ACT_NONE; g.out_f32 = 1;
             ASRB_TRY(launch_gemm_tc(g, st));
-            ASRB_TRY(launch_dwconv(w.G, DT_BF16, lw.dw15, lw.dw15_b, w.U, DT_BF16, B, T, D, 15, ACT_SILU, nullptr, st));
+            ASRB_TRY(launch_dwconv(w.G, DT_F32, lw.dw15, lw.dw15_b, w.U, DT_BF16, B, T, D, 15, ACT_SILU, nullptr, true, st));
             TcGemmArgs h{};
             h.A = (const __nv_bfloat16*)w.U; h.W = lw.w2_h; h.bias = lw.b2; h.res = (const __nv_bfloat16*)w.Y; h.out = w.H;
-            h.B = B; h.T = T; h.K = D; h.N = D; h.taps = 1; h.epilogue = TC_RES_ACT; h.act = ACT_GELU;
+            h.B = B; h.T = T; h.K = D; h.N = D; h.taps = 1; h.epilogue = TC_RES_ACT; h.act = ACT_GELU; h.out_f32 = 1;
             ASRB_TRY(launch_gemm_tc(h, st));
         } else {
             ASRB_TRY(launch_gemm_simt(w.X, DT_F32, lw.wc_f, lw.bc, nullptr, w.H, DT_F32, B, T, D, D, 3, ACT_NONE, st));
             ASRB_TRY(launch_layernorm(w.H, nullptr, lw.gamma, lw.beta, w.Y, DT_F32, rows, D, 1e-5f, st));
             ASRB_TRY(launch_gemm_simt(w.Y, DT_F32, lw.w1_f, lw.b1, nullptr, w.wide, DT_F32, B, T, D, 2 * D, 1, ACT_NONE, st));
             ASRB_TRY(launch_glu(w.wide, w.G, DT_F32, rows, D, st));
-            ASRB_TRY(launch_dwconv(w.G, DT_F32, lw.dw15, lw.dw15_b, w.U, DT_F32, B, T, D, 15, ACT_SILU, nullptr, st));
+            ASRB_TRY(launch_dwconv(w.G, DT_F32, lw.dw15, lw.dw15_b, w.U, DT_F32, B, T, D, 15, ACT_SILU, nullptr, false, st));
             ASRB_TRY(launch_gemm_simt(w.U, DT_F32, lw.w2_f, lw.b2, w.Y, w.H, DT_F32, B, T, D, D, 1, ACT_GELU, st));
         }
         // depthwise k3 + GELU (+ the next block's leading GELU; + sinusoids after the last block)
         void* dst = w.X; DType ddt = dt;
         if (last && direct_out) { dst = out; ddt = out_dtype == ASRB_BF16 ? DT_BF16 : DT_F32; }
-        ASRB_TRY(launch_dwconv(w.H, dt, lw.dw3, lw.dw3_b, dst, ddt, B, T, D, 3, last ? ACT_GELU : ACT_GELU_GELU,
-                               last ? e->pos_scales : nullptr, st));
+        // with the TransformerEncoderLayer the residual streams stay fp32 (x32 = fp32 copy of the stack output)
+        float* x32 = (last && bf && e->cfg.enc && tc_gemm_supported(D, D, TC_LN)) ? (float*)w.G : nullptr;
+        ASRB_TRY(launch_dwconv(w.H, bf ? DT_F32 : dt, lw.dw3, lw.dw3_b, dst, ddt, B, T, D, 3, last ? ACT_GELU : ACT_GELU_GELU,
+                               last ? w.pos : nullptr, bf, st, x32));
     }
     if (!e->cfg.enc) return ASRB_OK;
 
@@ -332,19 +342,22 @@ int encoder_body(asrb_encoder* e, const EncBuffers& w, const float* x_c1, int in
     const int H = e->cfg.head, F = e->cfg.ffn;
     const float scale = 1.0f / sqrtf((float)(D / H));
     const bool same = (out_dtype == ASRB_BF16) == bf;
-    void* fin = same ? out : w.G;
+    void* fin = same ? out : w.U;
     if (bf) {
         TcGemmArgs q{};
         q.A = (const __nv_bfloat16*)w.X; q.W = e->win_h; q.bias = e->bin; q.out = w.wide;
         q.B = B; q.T = T; q.K = D; q.N = 3 * D; q.taps = 1; q.epilogue = TC_BIAS_ACT; q.act = ACT_NONE;
         ASRB_TRY(launch_gemm_tc(q, st));
         ASRB_TRY(launch_attention_simt(w.wide, w.U, DT_BF16, B, T, D, H, scale, st));
-        ASRB_TRY(tc_gemm_ln((const __nv_bfloat16*)w.U, e->wo_h, e->bo, (const __nv_bfloat16*)w.X, e->n1g, e->n1b, w.Y, w.H, B, T, D, D, 1, st));
+        const bool fused_ln = tc_gemm_supported(D, D, TC_LN);
+        float* x32 = fused_ln ? (float*)w.G : nullptr;       // written by the last depthwise kernel
+        float* y32 = fused_ln ? (float*)w.H : nullptr;
+        ASRB_TRY(tc_gemm_ln((const __nv_bfloat16*)w.U, e->wo_h, e->bo, (const __nv_bfloat16*)w.X, e->n1g, e->n1b, w.Y, w.wide, B, T, D, D, 1, st, x32, y32));
         TcGemmArgs f1{};
         f1.A = (const __nv_bfloat16*)w.Y; f1.W = e->wf1_h; f1.bias = e->bf1; f1.out = w.ffn;
         f1.B = B; f1.T = T; f1.K = D; f1.N = F; f1.taps = 1; f1.epilogue = TC_BIAS_ACT; f1.act = ACT_RELU;
         ASRB_TRY(launch_gemm_tc(f1, st));
-        ASRB_TRY(tc_gemm_ln((const __nv_bfloat16*)w.ffn, e->wf2_h, e->bf2, (const __nv_bfloat16*)w.Y, e->n2g, e->n2b, fin, w.H, B, T, F, D, 1, st));
+        ASRB_TRY(tc_gemm_ln((const __nv_bfloat16*)w.ffn, e->wf2_h, e->bf2, (const __nv_bfloat16*)w.Y, e->n2g, e->n2b, fin, w.wide, B, T, F, D, 1, st, y32, nullptr));
         ProfScope ps("convert", st, 0.0, 6.0 * rows * D);
         if (!same) { convert_kernel<<<148 * 8, 256, 0, st>>>((const __nv_bfloat16*)fin, (float*)out, rows * D); ASRB_LAUNCH_CHECK(); }
     } else {

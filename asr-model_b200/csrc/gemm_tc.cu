@@ -28,7 +28,8 @@ template <int BN> struct TcCfg {
     static constexpr int B_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int XCH_BYTES = 2 * BM * 8;                       // LN partial sums, one float2 per row and half
-    static constexpr int SMEM = STAGES * STAGE_BYTES + STAGING_BYTES + XCH_BYTES + 128 /*barriers + tmem slot*/;
+    static constexpr int SMEM = STAGES * STAGE_BYTES + STAGING_BYTES + XCH_BYTES + 256 /*barriers + tmem slot*/;
+    static_assert((2 * STAGES + 4) * 8 + 4 <= 256, "barrier region");
     static_assert(SMEM <= 227 * 1024, "shared memory budget");
 };
 
@@ -107,18 +108,6 @@ __host__ __device__ constexpr uint32_t make_idesc(int bn) {
 }
 
 // --------------------------------- fast epilogue math -----------------------------------
-__device__ __forceinline__ float erf_fast(float x) {            // Abramowitz-Stegun 7.1.26, |err| < 1.5e-7
-    const float ax = fabsf(x);
-    const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
-    float p = fmaf(1.061405429f, t, -1.453152027f);
-    p = fmaf(p, t, 1.421413741f);
-    p = fmaf(p, t, -0.284496736f);
-    p = fmaf(p, t, 0.254829592f);
-    const float e = 1.0f - p * t * __expf(-ax * ax);
-    return copysignf(e, x);
-}
-__device__ __forceinline__ float gelu_fast(float x) { return 0.5f * x * (1.0f + erf_fast(x * 0.70710678118654752f)); }
-__device__ __forceinline__ float sigmoid_fast(float x) { return __frcp_rn(1.0f + __expf(-x)); }
 __device__ __forceinline__ float act_fast(float v, int act) {
     switch (act) {
         case ACT_GELU: return gelu_fast(v);
@@ -134,8 +123,8 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 }
 
 struct TcParams {
-    const float* bias; const __nv_bfloat16* res; const float* gamma; const float* beta;
-    int T, K, N, taps, act, tiles_per_utt, m_tiles, n_chunks, n_out;
+    const float* bias; const __nv_bfloat16* res; const float* res32; float* out32; const float* gamma; const float* beta;
+    int T, K, N, taps, act, tiles_per_utt, m_tiles, n_chunks, n_out, out_f32;
     float eps;
 };
 
@@ -150,6 +139,12 @@ __device__ __forceinline__ void stage_store32(unsigned char* staging, int r, int
         *reinterpret_cast<uint4*>(staging + r * 128 + ((chunk ^ (r & 7)) << 4)) = q;
     }
 }
+// 32 fp32 values of one row -> one 128-byte swizzled staging row (fp32 output tiles are 32 columns wide)
+__device__ __forceinline__ void stage_store32_f32(unsigned char* staging, int r, const float (&v)[32]) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+        *reinterpret_cast<float4*>(staging + r * 128 + ((i ^ (r & 7)) << 4)) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+}
 __device__ __forceinline__ void add_res32(float (&v)[32], const __nv_bfloat16* rp) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -158,6 +153,14 @@ __device__ __forceinline__ void add_res32(float (&v)[32], const __nv_bfloat16* r
 #pragma unroll
         for (int j = 0; j < 4; ++j) { const float2 f = __bfloat1622float2(h[j]); v[8 * i + 2 * j] += f.x; v[8 * i + 2 * j + 1] += f.y; }
     }
+}
+__device__ __forceinline__ void add_f32x32(float (&v)[32], const float* p) {     // plain (not read-only) loads
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { const float4 f = *(reinterpret_cast<const float4*>(p) + i); v[4 * i] += f.x; v[4 * i + 1] += f.y; v[4 * i + 2] += f.z; v[4 * i + 3] += f.w; }
+}
+__device__ __forceinline__ void store_f32x32(float* p, const float (&v)[32]) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) *(reinterpret_cast<float4*>(p) + i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
 }
 __device__ __forceinline__ void add_vec32(float (&v)[32], const float* p) {
 #pragma unroll
@@ -289,7 +292,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     float v[32];
                     tmem_ld32(acc + c, v);
                     add_vec32(v, p.bias + c);
-                    if (p.res && row_ok) add_res32(v, p.res + grow * p.N + c);
+                    if (row_ok) {
+                        if (p.res32) add_f32x32(v, p.res32 + grow * p.N + c);
+                        else if (p.res) add_res32(v, p.res + grow * p.N + c);
+                    }
 #pragma unroll
                     for (int i = 0; i < 32; ++i) { s1 += v[i]; s2 = fmaf(v[i], v[i], s2); }
                 }
@@ -305,11 +311,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     tmem_ld32(acc + c, v0);
                     tmem_ld32(acc + c + 32, v1);
                     add_vec32(v0, p.bias + c); add_vec32(v1, p.bias + c + 32);
-                    if (p.res && row_ok) { add_res32(v0, p.res + grow * p.N + c); add_res32(v1, p.res + grow * p.N + c + 32); }
+                    if (row_ok) {
+                        if (p.res32) { add_f32x32(v0, p.res32 + grow * p.N + c); add_f32x32(v1, p.res32 + grow * p.N + c + 32); }
+                        else if (p.res) { add_res32(v0, p.res + grow * p.N + c); add_res32(v1, p.res + grow * p.N + c + 32); }
+                    }
 #pragma unroll
                     for (int i = 0; i < 32; ++i) {
                         v0[i] = fmaf((v0[i] - mean) * rstd, __ldg(p.gamma + c + i), __ldg(p.beta + c + i));
                         v1[i] = fmaf((v1[i] - mean) * rstd, __ldg(p.gamma + c + 32 + i), __ldg(p.beta + c + 32 + i));
+                    }
+                    if (p.out32 && row_ok) {                                  // fp32 copy: the next residual stream
+                        store_f32x32(p.out32 + grow * p.N + c, v0); store_f32x32(p.out32 + grow * p.N + c + 32, v1);
                     }
                     if (leader) tma_wait_read0();
                     epi_bar(bar_id, 128);
@@ -347,6 +359,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
                             for (int i = 0; i < 32; ++i) { v0[i] = act_fast(v0[i], p.act); v1[i] = act_fast(v1[i], p.act); }
                         }
+                    }
+                    if (p.out_f32) {                                          // consumer is not an MMA: keep fp32
+#pragma unroll
+                        for (int hh = 0; hh < 2; ++hh) {
+                            if (leader) tma_wait_read0();
+                            epi_bar(bar_id, 128);
+                            stage_store32_f32(stg, r, hh ? v1 : v0);
+                            fence_async_smem();
+                            epi_bar(bar_id, 128);
+                            if (leader) { tma_store_3d(&map_out, stg_u32, gc + 32 * hh, t0, b); tma_commit(); }
+                        }
+                        continue;
                     }
                     if (leader) tma_wait_read0();                             // staging free again?
                     epi_bar(bar_id, 128);
@@ -402,6 +426,20 @@ static int make_act_map(CUtensorMap* m, const void* base, int64_t B, int64_t T, 
     if (r != CUDA_SUCCESS) return fail(ASRB_E_CUDA, "cuTensorMapEncodeTiled(activation C=%d T=%lld B=%lld) -> %d", C, (long long)T, (long long)B, (int)r);
     return ASRB_OK;
 }
+// [B][T][C] fp32 output: box 32 x 128 x 1 (128-byte rows), 128-byte swizzle
+static int make_out_f32_map(CUtensorMap* m, const void* base, int64_t B, int64_t T, int C) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return fail(ASRB_E_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+    cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)T, (cuuint64_t)B};
+    cuuint64_t strides[2] = {(cuuint64_t)C * 4, (cuuint64_t)T * C * 4};
+    cuuint32_t box[3] = {32, BM, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)base, dims, strides, box, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ASRB_E_CUDA, "cuTensorMapEncodeTiled(fp32 out C=%d) -> %d", C, (int)r);
+    return ASRB_OK;
+}
 static int make_w_map(CUtensorMap* m, const void* base, int N, int Ktot, int bn) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return fail(ASRB_E_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
@@ -451,17 +489,20 @@ int launch_gemm_tc(const TcGemmArgs& a, cudaStream_t st) {
     CUtensorMap ma, mw, mo;
     ASRB_TRY(make_act_map(&ma, a.A, a.B, a.T, a.K));
     ASRB_TRY(make_w_map(&mw, a.W, a.N, a.taps * a.K, bn));
-    ASRB_TRY(make_act_map(&mo, a.out, a.B, a.T, n_out));
+    if ((a.res32 || a.out32) && a.epilogue != TC_LN) return fail(ASRB_E_ARG, "tcgen05 GEMM: fp32 residual streams are a LayerNorm-epilogue feature");
+    if (a.out_f32 && a.epilogue == TC_LN) return fail(ASRB_E_ARG, "tcgen05 GEMM: LayerNorm epilogue stores bf16 only");
+    if (a.out_f32) ASRB_TRY(make_out_f32_map(&mo, a.out, a.B, a.T, n_out));
+    else ASRB_TRY(make_act_map(&mo, a.out, a.B, a.T, n_out));
     TcParams p;
-    p.bias = a.bias; p.res = a.res; p.gamma = a.gamma; p.beta = a.beta;
+    p.bias = a.bias; p.res = a.res; p.res32 = a.res32; p.out32 = a.out32; p.gamma = a.gamma; p.beta = a.beta;
     p.T = (int)a.T; p.K = a.K; p.N = a.N; p.taps = a.taps; p.act = a.act;
     p.tiles_per_utt = (int)((a.T + BM - 1) / BM);
     p.m_tiles = (int)(a.B * p.tiles_per_utt);
-    p.n_chunks = a.N / bn; p.n_out = n_out; p.eps = a.eps;
+    p.n_chunks = a.N / bn; p.n_out = n_out; p.eps = a.eps; p.out_f32 = a.out_f32;
     const int units = a.epilogue == TC_LN ? p.m_tiles : p.m_tiles * p.n_chunks;
     static const char* const tags[4] = {"gemm_tc_bias_act", "gemm_tc_glu", "gemm_tc_res_act", "gemm_tc_layernorm"};
     ProfScope ps(tags[a.epilogue], st, 2.0 * a.B * a.T * (double)a.N * a.K * a.taps,
-                 2.0 * a.B * a.T * ((double)a.K + n_out + (a.res ? n_out : 0)) + 2.0 * a.N * a.K * a.taps);
+                 2.0 * a.B * a.T * ((double)a.K + n_out * (a.out_f32 ? 2 : 1) + (a.res ? n_out : 0)) + 2.0 * a.N * a.K * a.taps);
 #define ASRB_TC(BN_, EPI_) return launch_one<BN_, EPI_>(ma, mw, mo, p, units, st)
     if (bn == 256) {
         switch (a.epilogue) {

@@ -95,7 +95,7 @@ typedef struct asrb_encoder asrb_encoder;
 
 typedef struct asrb_encoder_config {
     int32_t mels;        /* input channels of conv1 (80 | 128)                         */
-    int32_t dims;        /* D; multiple of 64 for ASRB_BF16                            */
+    int32_t dims;        /* D; multiple of 64 (ASRB_F32) or 128 (ASRB_BF16), <= 1024   */
     int32_t head;        /* heads of the optional TransformerEncoderLayer              */
     int32_t layer;       /* number of conv blocks                                      */
     int32_t enc;         /* 1 = TransformerEncoderLayer present (model.py:138)         */
