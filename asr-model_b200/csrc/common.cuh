@@ -66,18 +66,33 @@ __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __ex
 __device__ __forceinline__ float siluf_(float x) { return x * sigmoidf_(x); }
 
 // fast variants for the bf16 path (error far below one bf16 ulp)
-__device__ __forceinline__ float erf_fast(float x) {            // Abramowitz-Stegun 7.1.26, |err| < 1.5e-7
-    const float ax = fabsf(x);
-    const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
-    float p = fmaf(1.061405429f, t, -1.453152027f);
-    p = fmaf(p, t, 1.421413741f);
-    p = fmaf(p, t, -0.284496736f);
-    p = fmaf(p, t, 0.254829592f);
-    const float e = 1.0f - p * t * __expf(-ax * ax);
-    return copysignf(e, x);
+__device__ __forceinline__ float rcp_approx(float x) {           // MUFU.RCP, 1 ulp, no slow path
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
 }
-__device__ __forceinline__ float gelu_fast(float x) { return 0.5f * x * (1.0f + erf_fast(x * 0.70710678118654752f)); }
-__device__ __forceinline__ float sigmoid_fast(float x) { return __frcp_rn(1.0f + __expf(-x)); }
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float tanh_approx(float x) {          // MUFU.TANH, max relative error 2^-11
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// erf-GELU through one MUFU: 0.5 x (1 + tanh(x q(x^2))) with q fitted so that tanh(x q) = erf(x / sqrt 2)
+// (|formula error| < 3e-5 on the whole line; q is evaluated on |x| <= 7 where tanh has long saturated).
+// Total error incl. the MUFU bound: < 2.5e-4 |x| -- a few percent of a bf16 rounding of the result.
+__device__ __forceinline__ float gelu_fast(float x) {
+    const float xc = fminf(fmaxf(x, -7.0f), 7.0f);
+    const float s = xc * xc;
+    const float q = fmaf(fmaf(-3.58867440e-04f, s, 3.70510348e-02f), s, 7.97457818e-01f);
+    const float hx = 0.5f * x;
+    return fmaf(hx, tanh_approx(xc * q), hx);
+}
+// sigmoid(x) = 0.5 + 0.5 tanh(x / 2)
+__device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(0.5f, tanh_approx(0.5f * x), 0.5f); }
 
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll

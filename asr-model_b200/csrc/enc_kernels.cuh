@@ -54,7 +54,9 @@ int launch_rotary_headnorm(float* x, int64_t ld, const float* xa, const float* l
                            int64_t B, int64_t T, int D, int H, float pre_scale, cudaStream_t st);
 
 // ---- tcgen05 / TMEM / TMA GEMM (gemm_tc.cu), bf16 operands, fp32 accumulate -----------------
-enum TcEpilogue { TC_BIAS_ACT = 0, TC_GLU = 1, TC_RES_ACT = 2, TC_LN = 3 };
+enum TcEpilogue { TC_BIAS_ACT = 0, TC_GLU = 1, TC_RES_ACT = 2, TC_LN = 3,
+                  TC_GLU_DW = 4,        // GLU -> depthwise conv down the frames (+folded BN) -> act2
+                  TC_RES_ACT_DW = 5 };  // bias + residual + act -> depthwise conv -> act2 (+ sinusoids)
 
 struct TcGemmArgs {
     const __nv_bfloat16* A;      // [B][T][K] channels-last
@@ -69,6 +71,9 @@ struct TcGemmArgs {
     int64_t B, T;
     int K, N, taps;
     int epilogue; int act; float eps;
+    const float* dw_w;           // fused depthwise epilogues: [kw][Nout] taps, [Nout] bias, kw in {3, 15}
+    const float* dw_b; int dw_kw; int dw_act;
+    const float* pos;            // optional [T][Nout] sinusoid table added after dw_act
     int out_f32;                 // store fp32 (consumer is a depthwise conv, not an MMA); not with TC_LN
 };
 bool tc_gemm_supported(int K, int N, int epilogue);

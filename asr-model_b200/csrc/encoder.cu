@@ -311,14 +311,31 @@ int encoder_body(asrb_encoder* e, const EncBuffers& w, const float* x_c1, int in
         const bool last = i == L - 1;
         if (bf) {
             ASRB_TRY(tc_gemm_ln((const __nv_bfloat16*)w.X, lw.wc_h, lw.bc, nullptr, lw.gamma, lw.beta, w.Y, w.H, B, T, D, D, 3, st));
+            // point1 + GLU + depthwise-15 (BatchNorm folded) + SiLU in one kernel: Y -> U
             TcGemmArgs g{};
-            g.A = (const __nv_bfloat16*)w.Y; g.W = lw.w1_h; g.bias = lw.b1_glu; g.out = w.G;
-            g.B = B; g.T = T; g.K = D; g.N = 2 * D; g.taps = 1; g.epilogue = TC_GLU; g.act = ACT_NONE; g.out_f32 = 1;
+            g.A = (const __nv_bfloat16*)w.Y; g.W = lw.w1_h; g.bias = lw.b1_glu; g.out = w.U;
+            g.B = B; g.T = T; g.K = D; g.N = 2 * D; g.taps = 1; g.epilogue = TC_GLU_DW; g.act = ACT_NONE;
+            g.dw_w = lw.dw15; g.dw_b = lw.dw15_b; g.dw_kw = 15; g.dw_act = ACT_SILU;
             ASRB_TRY(launch_gemm_tc(g, st));
-            ASRB_TRY(launch_dwconv(w.G, DT_F32, lw.dw15, lw.dw15_b, w.U, DT_BF16, B, T, D, 15, ACT_SILU, nullptr, true, st));
             TcGemmArgs h{};
-            h.A = (const __nv_bfloat16*)w.U; h.W = lw.w2_h; h.bias = lw.b2; h.res = (const __nv_bfloat16*)w.Y; h.out = w.H;
-            h.B = B; h.T = T; h.K = D; h.N = D; h.taps = 1; h.epilogue = TC_RES_ACT; h.act = ACT_GELU; h.out_f32 = 1;
+            h.A = (const __nv_bfloat16*)w.U; h.W = lw.w2_h; h.bias = lw.b2; h.res = (const __nv_bfloat16*)w.Y;
+            h.B = B; h.T = T; h.K = D; h.N = D; h.taps = 1; h.act = ACT_GELU;
+            if (tc_gemm_supported(D, D, TC_RES_ACT_DW)) {
+                // point2 + residual + GELU + depthwise-3 + GELU (+ next block's GELU | + sinusoids): U, Y -> X
+                const bool to_out = last && !e->cfg.enc && out_dtype == ASRB_BF16;
+                h.epilogue = TC_RES_ACT_DW; h.out = to_out ? out : w.X;
+                h.dw_w = lw.dw3; h.dw_b = lw.dw3_b; h.dw_kw = 3; h.dw_act = last ? ACT_GELU : ACT_GELU_GELU;
+                h.pos = last ? w.pos : nullptr;
+                h.out32 = (last && e->cfg.enc && tc_gemm_supported(D, D, TC_LN)) ? (float*)w.G : nullptr;
+                ASRB_TRY(launch_gemm_tc(h, st));
+                if (last && !e->cfg.enc && out_dtype != ASRB_BF16) {
+                    ProfScope ps("convert", st, 0.0, 6.0 * rows * D);
+                    convert_kernel<<<148 * 8, 256, 0, st>>>((const __nv_bfloat16*)w.X, (float*)out, rows * D);
+                    ASRB_LAUNCH_CHECK();
+                }
+                continue;
+            }
+            h.epilogue = TC_RES_ACT; h.out = w.H; h.out_f32 = 1;
             ASRB_TRY(launch_gemm_tc(h, st));
         } else {
             ASRB_TRY(launch_gemm_simt(w.X, DT_F32, lw.wc_f, lw.bc, nullptr, w.H, DT_F32, B, T, D, D, 3, ACT_NONE, st));

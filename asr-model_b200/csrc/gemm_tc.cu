@@ -18,17 +18,21 @@ namespace asrb {
 
 static constexpr int BM = 128;          // rows (frames) per tile = TMEM lanes
 static constexpr int BK = 64;           // bf16 per 128-byte swizzle row
-static constexpr int EPI_WARPS = 8;
-static constexpr int NUM_THREADS = 64 + EPI_WARPS * 32;
-static constexpr int STAGING_BYTES = 2 * BM * 128;      // one 128x64 bf16 chunk per column half
+// Per epilogue group (4 warps = 128 threads = one row each): one 17 KB scratch tile that is, in
+// turn, the fp32 exchange buffer [128][33] of the fused depthwise epilogues and the staging
+// tile of the TMA store ([128][64] bf16 swizzled / [128][32] fp32 swizzled / [rows][32] bf16).
+static constexpr int GROUP_SCRATCH = 17 * 1024;
+static constexpr int XPITCH = 33;       // fp32 words per exchange-buffer row (bank-conflict-free both ways)
 
 template <int BN> struct TcCfg {
-    static constexpr int STAGES = BN == 256 ? 4 : 6;
+    static constexpr int NG = BN == 256 ? 4 : 2;                       // epilogue groups (column slices)
+    static constexpr int THREADS = 64 + NG * 128;
+    static constexpr int STAGES = BN == 256 ? 3 : 5;
     static constexpr int A_BYTES = BM * BK * 2;
     static constexpr int B_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int XCH_BYTES = 2 * BM * 8;                       // LN partial sums, one float2 per row and half
-    static constexpr int SMEM = STAGES * STAGE_BYTES + STAGING_BYTES + XCH_BYTES + 256 /*barriers + tmem slot*/;
+    static constexpr int XCH_BYTES = NG * BM * 8;                      // LN partial sums, one float2 per row and group
+    static constexpr int SMEM = STAGES * STAGE_BYTES + NG * GROUP_SCRATCH + XCH_BYTES + 256 /*barriers + tmem slot*/;
     static_assert((2 * STAGES + 4) * 8 + 4 <= 256, "barrier region");
     static_assert(SMEM <= 227 * 1024, "shared memory budget");
 };
@@ -117,6 +121,27 @@ __device__ __forceinline__ float act_fast(float v, int act) {
         default: return v;
     }
 }
+__device__ __forceinline__ void act_fast32(float (&v)[32], int act) {      // switch hoisted out of the element loop
+    switch (act) {
+        case ACT_GELU:
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = gelu_fast(v[i]);
+            break;
+        case ACT_GELU_GELU:
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = gelu_fast(gelu_fast(v[i]));
+            break;
+        case ACT_SILU:
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = v[i] * sigmoid_fast(v[i]);
+            break;
+        case ACT_RELU:
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+            break;
+        default: break;
+    }
+}
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&h);
@@ -126,6 +151,9 @@ struct TcParams {
     const float* bias; const __nv_bfloat16* res; const float* res32; float* out32; const float* gamma; const float* beta;
     int T, K, N, taps, act, tiles_per_utt, m_tiles, n_chunks, n_out, out_f32;
     float eps;
+    // fused depthwise epilogue (TC_GLU_DW / TC_RES_ACT_DW): a tile's 128 rows are frames
+    // [t0 - halo, t0 + 128 - halo); rows_out = 128 - 2*halo frames are produced per tile
+    const float* dw_w; const float* dw_b; const float* pos; int kw, halo, rows_out, act2;
 };
 
 // 32 fp32 values of one row -> 32 bf16 into the swizzled staging tile (row r, columns cb..cb+31 of 64)
@@ -167,16 +195,49 @@ __device__ __forceinline__ void add_vec32(float (&v)[32], const float* p) {
     for (int i = 0; i < 8; ++i) { const float4 f = __ldg(reinterpret_cast<const float4*>(p) + i); v[4 * i] += f.x; v[4 * i + 1] += f.y; v[4 * i + 2] += f.z; v[4 * i + 3] += f.w; }
 }
 
+// ---- fused depthwise epilogue helpers ----------------------------------------------------
+// xbuf: [128 rows][XPITCH] fp32.  Pitch 33 makes both the row-per-thread writes (phase 1) and the
+// column-per-thread reads (phase 2) bank-conflict free, and every access is base + immediate.
+__device__ __forceinline__ void xbuf_store_row(float* xrow, const float (&v)[32]) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) xrow[i] = v[i];
+}
+
+// Phase 2: this thread owns column `c` and output rows [o0, o0 + 32) of the tile; the input row of
+// output o and tap j is o + j.  Results stay in registers (the buffer is about to be reused).
+template <int KW>
+__device__ __forceinline__ void dw_columns(const float* xcol /* &xbuf[o0][c] */, int o0, const float* __restrict__ w,
+                                           int D, int gcol, float bias, int act2, float (&out)[32]) {
+    float wv[KW];
+#pragma unroll
+    for (int j = 0; j < KW; ++j) wv[j] = __ldg(w + (int64_t)j * D + gcol);
+    float win[KW];
+    const int lim = BM - o0;                                   // rows available below o0
+#pragma unroll
+    for (int j = 0; j < KW - 1; ++j) win[j + 1] = (j < lim) ? xcol[j * XPITCH] : 0.f;
+#pragma unroll
+    for (int o = 0; o < 32; ++o) {
+#pragma unroll
+        for (int j = 0; j < KW - 1; ++j) win[j] = win[j + 1];
+        win[KW - 1] = (o + KW - 1 < lim) ? xcol[(o + KW - 1) * XPITCH] : 0.f;
+        float a = bias;
+#pragma unroll
+        for (int j = 0; j < KW; ++j) a = fmaf(wv[j], win[j], a);
+        out[o] = a;
+    }
+    act_fast32(out, act2);
+}
+
 template <int BN, int EPI>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(TcCfg<BN>::THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                const __grid_constant__ CUtensorMap map_out, const TcParams p) {
     using C = TcCfg<BN>;
-    constexpr int STAGES = C::STAGES;
+    constexpr int STAGES = C::STAGES, NG = C::NG;
     extern __shared__ __align__(1024) unsigned char smem[];                  // SWIZZLE_128B tiles need 1024-B alignment
-    unsigned char* staging = smem + STAGES * C::STAGE_BYTES;                 // 2 x [128][128 B]
-    float2* s_xch = reinterpret_cast<float2*>(staging + STAGING_BYTES);      // [2][BM] LN partial (sum, sumsq)
-    uint64_t* bars = reinterpret_cast<uint64_t*>(staging + STAGING_BYTES + C::XCH_BYTES);
+    unsigned char* scratch = smem + STAGES * C::STAGE_BYTES;                 // NG x GROUP_SCRATCH
+    float2* s_xch = reinterpret_cast<float2*>(scratch + NG * GROUP_SCRATCH); // [NG][BM] LN partial (sum, sumsq)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(scratch + NG * GROUP_SCRATCH + C::XCH_BYTES);
     // bars: full[STAGES], empty[STAGES], tfull[2], tempty[2]
     const uint32_t bar0 = smem_u32(bars);
     auto full_bar = [&](int s) { return bar0 + 8u * s; };
@@ -186,8 +247,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const bool is_ln = EPI == TC_LN;
-    const int nbu = is_ln ? p.n_chunks : 1;                                  // chunks per unit
+    constexpr bool is_ln = EPI == TC_LN;
+    const int nbu = is_ln ? p.n_chunks : 1;                                  // accumulator chunks per unit
     const int units = is_ln ? p.m_tiles : p.m_tiles * p.n_chunks;
     const int acc_stages = (512 / (nbu * BN)) >= 2 ? 2 : 1;
     const int kb_per_tap = p.K / BK;
@@ -201,7 +262,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), EPI_WARPS * 32); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), NG * 128); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {                                                         // TMEM: all 512 columns
@@ -220,7 +281,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             for (int u = blockIdx.x; u < units; u += gridDim.x) {
                 const int m = is_ln ? u : u / p.n_chunks;
                 const int nb0 = is_ln ? 0 : u % p.n_chunks;
-                const int b = m / p.tiles_per_utt, t0 = (m % p.tiles_per_utt) * BM;
+                const int b = m / p.tiles_per_utt, t0 = (m % p.tiles_per_utt) * p.rows_out - p.halo;
                 for (int j = 0; j < nbu; ++j) {
                     const int n0 = (nb0 + j) * BN;
                     for (int kb = 0; kb < num_kb; ++kb) {
@@ -264,29 +325,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
     } else {
         // ================================ epilogue ====================================
+        // NG groups of 4 warps; a group owns a slice of the tile's columns, its warps own the four
+        // TMEM lane quadrants (warp % 4), so in phase 1 a thread is one row of the tile.
         const int ew = warp - 2;
-        const int quad = warp & 3;                        // TMEM lane quadrant this warp may read
-        const int half = ew >> 2;                         // column half
+        const int quad = warp & 3;
+        const int group = ew >> 2;
         const int r = quad * 32 + lane;                   // row inside the tile
-        const bool leader = (ew & 3) == 0 && lane == 0;   // issues this half's TMA stores
-        unsigned char* stg = staging + half * (BM * 128);
+        const bool leader = (ew & 3) == 0 && lane == 0;   // issues this group's TMA stores
+        unsigned char* stg = scratch + group * GROUP_SCRATCH;
         const uint32_t stg_u32 = smem_u32(stg);
-        const int bar_id = 1 + half;
+        const int bar_id = 1 + group;
         int it = 0;
         for (int u = blockIdx.x; u < units; u += gridDim.x, ++it) {
             const int m = is_ln ? u : u / p.n_chunks;
             const int nb0 = is_ln ? 0 : u % p.n_chunks;
-            const int b = m / p.tiles_per_utt, t0 = (m % p.tiles_per_utt) * BM;
+            const int b = m / p.tiles_per_utt, t0 = (m % p.tiles_per_utt) * p.rows_out - p.halo;   // frame of tile row 0
             const int a = it % acc_stages;
             const uint32_t aph = (uint32_t)(it / acc_stages) & 1u;
-            const bool row_ok = t0 + r < p.T;
+            const bool row_ok = t0 + r >= 0 && t0 + r < p.T;
             const int64_t grow = (int64_t)b * p.T + t0 + r;
             mbar_wait(tfull_bar(a), aph);
             tc_fence_after();
             const uint32_t acc = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(a * nbu * BN);
 
             if (EPI == TC_LN) {
-                const int ncols = p.N / 2, c_begin = half * ncols;            // this thread's slice of the row
+                // ---- bias (+ residual) + LayerNorm over the whole row (row = nbu chunks side by side) ----
+                const int ncols = p.N / NG, c_begin = group * ncols;          // this thread's slice of the row
                 float s1 = 0.f, s2 = 0.f;
                 for (int c = c_begin; c < c_begin + ncols; c += 32) {
                     float v[32];
@@ -299,86 +363,132 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
                     for (int i = 0; i < 32; ++i) { s1 += v[i]; s2 = fmaf(v[i], v[i], s2); }
                 }
-                s_xch[half * BM + r] = make_float2(s1, s2);
-                epi_bar(3, EPI_WARPS * 32);
-                const float2 o = s_xch[(half ^ 1) * BM + r];
-                epi_bar(3, EPI_WARPS * 32);                                   // partner has read before the next tile writes
-                const float mean = (s1 + o.x) / (float)p.N;
-                const float var = fmaxf((s2 + o.y) / (float)p.N - mean * mean, 0.f);
-                const float rstd = rsqrtf(var + p.eps);
-                for (int c = c_begin; c < c_begin + ncols; c += 64) {
-                    float v0[32], v1[32];
-                    tmem_ld32(acc + c, v0);
-                    tmem_ld32(acc + c + 32, v1);
-                    add_vec32(v0, p.bias + c); add_vec32(v1, p.bias + c + 32);
+                s_xch[group * BM + r] = make_float2(s1, s2);
+                epi_bar(NG + 1, NG * 128);
+                float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+                for (int gq = 0; gq < NG; ++gq) { const float2 o = s_xch[gq * BM + r]; t1 += o.x; t2 += o.y; }
+                epi_bar(NG + 1, NG * 128);                                    // all partners have read before the next tile writes
+                const float mean = t1 / (float)p.N;
+                const float rstd = rsqrtf(fmaxf(t2 / (float)p.N - mean * mean, 0.f) + p.eps);
+                for (int c = c_begin; c < c_begin + ncols; c += 32) {
+                    float v[32];
+                    tmem_ld32(acc + c, v);
+                    add_vec32(v, p.bias + c);
                     if (row_ok) {
-                        if (p.res32) { add_f32x32(v0, p.res32 + grow * p.N + c); add_f32x32(v1, p.res32 + grow * p.N + c + 32); }
-                        else if (p.res) { add_res32(v0, p.res + grow * p.N + c); add_res32(v1, p.res + grow * p.N + c + 32); }
+                        if (p.res32) add_f32x32(v, p.res32 + grow * p.N + c);
+                        else if (p.res) add_res32(v, p.res + grow * p.N + c);
                     }
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        v0[i] = fmaf((v0[i] - mean) * rstd, __ldg(p.gamma + c + i), __ldg(p.beta + c + i));
-                        v1[i] = fmaf((v1[i] - mean) * rstd, __ldg(p.gamma + c + 32 + i), __ldg(p.beta + c + 32 + i));
+                    for (int i = 0; i < 8; ++i) {
+                        const float4 gm = __ldg(reinterpret_cast<const float4*>(p.gamma + c) + i);
+                        const float4 bt = __ldg(reinterpret_cast<const float4*>(p.beta + c) + i);
+                        v[4 * i + 0] = fmaf((v[4 * i + 0] - mean) * rstd, gm.x, bt.x);
+                        v[4 * i + 1] = fmaf((v[4 * i + 1] - mean) * rstd, gm.y, bt.y);
+                        v[4 * i + 2] = fmaf((v[4 * i + 2] - mean) * rstd, gm.z, bt.z);
+                        v[4 * i + 3] = fmaf((v[4 * i + 3] - mean) * rstd, gm.w, bt.w);
                     }
-                    if (p.out32 && row_ok) {                                  // fp32 copy: the next residual stream
-                        store_f32x32(p.out32 + grow * p.N + c, v0); store_f32x32(p.out32 + grow * p.N + c + 32, v1);
+                    if (p.out32 && row_ok) store_f32x32(p.out32 + grow * p.N + c, v);   // fp32 copy: the next residual stream
+                    const int cb = (c - c_begin) & 32;                        // which half of the 64-column staging tile
+                    if (cb == 0) { if (leader) tma_wait_read0(); epi_bar(bar_id, 128); }
+                    stage_store32(stg, r, cb, v);
+                    if (cb == 32) {
+                        fence_async_smem();
+                        epi_bar(bar_id, 128);
+                        if (leader) { tma_store_3d(&map_out, stg_u32, c - 32, t0, b); tma_commit(); }
                     }
-                    if (leader) tma_wait_read0();
+                }
+            } else if (EPI == TC_GLU_DW || EPI == TC_RES_ACT_DW) {
+                // phase 1 (thread = row): accumulator -> bias (+GLU | +residual, act) -> xbuf (fp32)
+                // phase 2 (thread = column x 32-row slice): depthwise conv down the tile rows + act2
+                //          (+ sinusoids) -> registers -> bf16 tile [rows_out][32] -> TMA store
+                constexpr bool GLU = EPI == TC_GLU_DW;
+                constexpr int OUT_PER_TILE = GLU ? BN / 2 : BN;
+                constexpr int COLS = OUT_PER_TILE / NG;                       // per group
+                float* xbuf = reinterpret_cast<float*>(stg);
+                const int slice = ew & 3;                                     // phase-2 row slice of this warp
+                for (int cc = 0; cc < COLS; cc += 32) {
+                    const int tc0 = group * COLS + cc;                        // column inside the accumulator
+                    const int gc = nb0 * OUT_PER_TILE + tc0;                  // global output column of this chunk
+                    float v[32];
+                    tmem_ld32(acc + tc0, v);
+                    if (GLU) {
+                        float gt[32];
+                        tmem_ld32(acc + BN / 2 + tc0, gt);
+                        const int vb = nb0 * BN + tc0;
+                        add_vec32(v, p.bias + vb);
+                        add_vec32(gt, p.bias + vb + BN / 2);
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] *= sigmoid_fast(gt[i]);
+                    } else {
+                        add_vec32(v, p.bias + gc);
+                        if (row_ok) add_res32(v, p.res + grow * p.n_out + gc);
+                        act_fast32(v, p.act);
+                    }
+                    if (!row_ok) {                                            // conv zero padding outside [0, T)
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] = 0.f;
+                    }
+                    if (leader) tma_wait_read0();                             // previous TMA store has read the tile
                     epi_bar(bar_id, 128);
-                    stage_store32(stg, r, 0, v0);
-                    stage_store32(stg, r, 32, v1);
+                    xbuf_store_row(xbuf + r * XPITCH, v);
+                    epi_bar(bar_id, 128);
+                    float o[32];
+                    const int gcol = gc + lane;
+                    const float dwb = __ldg(p.dw_b + gcol);
+                    const float* xcol = xbuf + slice * 32 * XPITCH + lane;
+                    if (p.kw == 15) dw_columns<15>(xcol, slice * 32, p.dw_w, p.n_out, gcol, dwb, p.act2, o);
+                    else dw_columns<3>(xcol, slice * 32, p.dw_w, p.n_out, gcol, dwb, p.act2, o);
+                    const int tout0 = t0 + p.halo + slice * 32;               // frame of this thread's first output row
+                    const int nrow = min(min(32, p.rows_out - slice * 32), p.T - tout0);   // valid outputs of this thread
+                    if (p.pos) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (i < nrow) o[i] += __ldg(p.pos + (int64_t)(tout0 + i) * p.n_out + gcol);
+                    }
+                    if (p.out32) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (i < nrow) p.out32[((int64_t)b * p.T + tout0 + i) * p.n_out + gcol] = o[i];
+                    }
+                    epi_bar(bar_id, 128);                                     // everyone is done reading xbuf
+                    __nv_bfloat16* tile = reinterpret_cast<__nv_bfloat16*>(stg) + slice * 32 * 32 + lane;   // [rows_out][32] bf16
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (slice * 32 + i < p.rows_out) tile[i * 32] = __float2bfloat16_rn(o[i]);
                     fence_async_smem();
                     epi_bar(bar_id, 128);
-                    if (leader) { tma_store_3d(&map_out, stg_u32, c, t0, b); tma_commit(); }
+                    if (leader) { tma_store_3d(&map_out, stg_u32, gc, t0 + p.halo, b); tma_commit(); }
                 }
             } else {
-                constexpr int OUT_PER_TILE = EPI == TC_GLU ? BN / 2 : BN;     // output columns per tile
-                constexpr int COLS = OUT_PER_TILE / 2;                        // per column half
-                const int out0 = nb0 * OUT_PER_TILE + half * COLS;            // first global output column
-                for (int cc = 0; cc < COLS; cc += 64) {
-                    float v0[32], v1[32];
-                    const int tc0 = half * COLS + cc;                         // column inside the accumulator
-                    tmem_ld32(acc + tc0, v0);
-                    tmem_ld32(acc + tc0 + 32, v1);
-                    const int gc = out0 + cc;                                 // global output column
-                    if (EPI == TC_GLU) {
-                        float g0[32], g1[32];
-                        tmem_ld32(acc + BN / 2 + tc0, g0);
-                        tmem_ld32(acc + BN / 2 + tc0 + 32, g1);
-                        const int vb = nb0 * BN + tc0;                        // packed bias index (value | gate per tile)
-                        add_vec32(v0, p.bias + vb); add_vec32(v1, p.bias + vb + 32);
-                        add_vec32(g0, p.bias + vb + BN / 2); add_vec32(g1, p.bias + vb + BN / 2 + 32);
+                // ---- bias (+ residual) + activation; 64 output columns per group ----
+                constexpr int COLS = BN / NG;
+                static_assert(COLS == 64, "plain epilogue: one 64-column staging tile per group");
+                const int tc0 = group * COLS;                                 // column inside the accumulator
+                const int gc = nb0 * BN + tc0;                                // global output column
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) { v0[i] *= sigmoid_fast(g0[i]); v1[i] *= sigmoid_fast(g1[i]); }
+                for (int hh = 0; hh < 2; ++hh) {
+                    float v[32];
+                    tmem_ld32(acc + tc0 + 32 * hh, v);
+                    add_vec32(v, p.bias + gc + 32 * hh);
+                    if (EPI == TC_RES_ACT && row_ok) add_res32(v, p.res + grow * p.n_out + gc + 32 * hh);
+                    act_fast32(v, p.act);
+                    if (p.out_f32) {                                          // consumer is not an MMA: keep fp32 (32-column boxes)
+                        if (leader) tma_wait_read0();
+                        epi_bar(bar_id, 128);
+                        stage_store32_f32(stg, r, v);
+                        fence_async_smem();
+                        epi_bar(bar_id, 128);
+                        if (leader) { tma_store_3d(&map_out, stg_u32, gc + 32 * hh, t0, b); tma_commit(); }
                     } else {
-                        add_vec32(v0, p.bias + gc); add_vec32(v1, p.bias + gc + 32);
-                        if (EPI == TC_RES_ACT && row_ok) {
-                            add_res32(v0, p.res + grow * p.n_out + gc); add_res32(v1, p.res + grow * p.n_out + gc + 32);
-                        }
-                        if (p.act != ACT_NONE) {
-#pragma unroll
-                            for (int i = 0; i < 32; ++i) { v0[i] = act_fast(v0[i], p.act); v1[i] = act_fast(v1[i], p.act); }
-                        }
-                    }
-                    if (p.out_f32) {                                          // consumer is not an MMA: keep fp32
-#pragma unroll
-                        for (int hh = 0; hh < 2; ++hh) {
-                            if (leader) tma_wait_read0();
-                            epi_bar(bar_id, 128);
-                            stage_store32_f32(stg, r, hh ? v1 : v0);
+                        if (hh == 0) { if (leader) tma_wait_read0(); epi_bar(bar_id, 128); }
+                        stage_store32(stg, r, 32 * hh, v);
+                        if (hh == 1) {
                             fence_async_smem();
                             epi_bar(bar_id, 128);
-                            if (leader) { tma_store_3d(&map_out, stg_u32, gc + 32 * hh, t0, b); tma_commit(); }
+                            if (leader) { tma_store_3d(&map_out, stg_u32, gc, t0, b); tma_commit(); }
                         }
-                        continue;
                     }
-                    if (leader) tma_wait_read0();                             // staging free again?
-                    epi_bar(bar_id, 128);
-                    stage_store32(stg, r, 0, v0);
-                    stage_store32(stg, r, 32, v1);
-                    fence_async_smem();
-                    epi_bar(bar_id, 128);
-                    if (leader) { tma_store_3d(&map_out, stg_u32, gc, t0, b); tma_commit(); }
                 }
             }
             tc_fence_before();
@@ -440,6 +550,20 @@ static int make_out_f32_map(CUtensorMap* m, const void* base, int64_t B, int64_t
     if (r != CUDA_SUCCESS) return fail(ASRB_E_CUDA, "cuTensorMapEncodeTiled(fp32 out C=%d) -> %d", C, (int)r);
     return ASRB_OK;
 }
+// bf16 output of the fused depthwise epilogues: box 32 cols x rows_out frames, plain 64-byte rows
+static int make_dw_out_map(CUtensorMap* m, const void* base, int64_t B, int64_t T, int C, int rows_out) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return fail(ASRB_E_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+    cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)T, (cuuint64_t)B};
+    cuuint64_t strides[2] = {(cuuint64_t)C * 2, (cuuint64_t)T * C * 2};
+    cuuint32_t box[3] = {32, (cuuint32_t)rows_out, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)base, dims, strides, box, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ASRB_E_CUDA, "cuTensorMapEncodeTiled(dw out C=%d rows=%d) -> %d", C, rows_out, (int)r);
+    return ASRB_OK;
+}
 static int make_w_map(CUtensorMap* m, const void* base, int N, int Ktot, int bn) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return fail(ASRB_E_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
@@ -455,7 +579,7 @@ static int make_w_map(CUtensorMap* m, const void* base, int N, int Ktot, int bn)
 }
 
 static int pick_bn(int N, int epi) {
-    if (epi == TC_GLU) return 256;
+    if (epi == TC_GLU_DW || epi == TC_RES_ACT_DW) return 256;
     if (epi == TC_LN) return (N % 256 == 0) ? 256 : 128;
     return (N % 256 == 0) ? 256 : 128;
 }
@@ -463,7 +587,8 @@ int tc_glu_tile_n(int) { return 256; }
 
 bool tc_gemm_supported(int K, int N, int epi) {
     if (K % 64 != 0 || N % 128 != 0) return false;
-    if (epi == TC_GLU && N % 256 != 0) return false;
+    if (epi == TC_GLU) return false;                 // superseded by TC_GLU_DW
+    if ((epi == TC_GLU_DW || epi == TC_RES_ACT_DW) && N % 256 != 0) return false;
     if (epi == TC_LN && N > 512) return false;
     return true;
 }
@@ -475,7 +600,7 @@ static int launch_one(const CUtensorMap& ma, const CUtensorMap& mw, const CUtens
     ASRB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::SMEM));
     int grid = sm_count();
     if (grid > units) grid = units;
-    kern<<<grid, NUM_THREADS, TcCfg<BN>::SMEM, st>>>(ma, mw, mo, p);
+    kern<<<grid, TcCfg<BN>::THREADS, TcCfg<BN>::SMEM, st>>>(ma, mw, mo, p);
     ASRB_LAUNCH_CHECK();
     return ASRB_OK;
 }
@@ -485,31 +610,41 @@ int launch_gemm_tc(const TcGemmArgs& a, cudaStream_t st) {
         return fail(ASRB_E_ARG, "tcgen05 GEMM: unsupported shape K=%d N=%d epilogue=%d", a.K, a.N, a.epilogue);
     if (a.B <= 0 || a.T <= 0) return ASRB_OK;
     const int bn = pick_bn(a.N, a.epilogue);
-    const int n_out = a.epilogue == TC_GLU ? a.N / 2 : a.N;
+    const bool glu = a.epilogue == TC_GLU || a.epilogue == TC_GLU_DW;
+    const bool dw = a.epilogue == TC_GLU_DW || a.epilogue == TC_RES_ACT_DW;
+    const int n_out = glu ? a.N / 2 : a.N;
+    if (dw && ((a.dw_kw != 3 && a.dw_kw != 15) || !a.dw_w || !a.dw_b || a.out_f32 || a.taps != 1))
+        return fail(ASRB_E_ARG, "tcgen05 GEMM: bad fused-depthwise arguments");
+    if (a.epilogue == TC_RES_ACT_DW && !a.res) return fail(ASRB_E_ARG, "tcgen05 GEMM: residual required");
+    const int halo = dw ? a.dw_kw / 2 : 0, rows_out = BM - 2 * halo;
     CUtensorMap ma, mw, mo;
     ASRB_TRY(make_act_map(&ma, a.A, a.B, a.T, a.K));
     ASRB_TRY(make_w_map(&mw, a.W, a.N, a.taps * a.K, bn));
-    if ((a.res32 || a.out32) && a.epilogue != TC_LN) return fail(ASRB_E_ARG, "tcgen05 GEMM: fp32 residual streams are a LayerNorm-epilogue feature");
+    if ((a.res32 || (a.out32 && !dw)) && a.epilogue != TC_LN) return fail(ASRB_E_ARG, "tcgen05 GEMM: fp32 residual streams are a LayerNorm-epilogue feature");
     if (a.out_f32 && a.epilogue == TC_LN) return fail(ASRB_E_ARG, "tcgen05 GEMM: LayerNorm epilogue stores bf16 only");
-    if (a.out_f32) ASRB_TRY(make_out_f32_map(&mo, a.out, a.B, a.T, n_out));
+    if (dw) ASRB_TRY(make_dw_out_map(&mo, a.out, a.B, a.T, n_out, rows_out));
+    else if (a.out_f32) ASRB_TRY(make_out_f32_map(&mo, a.out, a.B, a.T, n_out));
     else ASRB_TRY(make_act_map(&mo, a.out, a.B, a.T, n_out));
     TcParams p;
     p.bias = a.bias; p.res = a.res; p.res32 = a.res32; p.out32 = a.out32; p.gamma = a.gamma; p.beta = a.beta;
     p.T = (int)a.T; p.K = a.K; p.N = a.N; p.taps = a.taps; p.act = a.act;
-    p.tiles_per_utt = (int)((a.T + BM - 1) / BM);
+    p.dw_w = a.dw_w; p.dw_b = a.dw_b; p.pos = a.pos; p.kw = a.dw_kw; p.halo = halo; p.rows_out = rows_out; p.act2 = a.dw_act;
+    p.tiles_per_utt = (int)((a.T + rows_out - 1) / rows_out);
     p.m_tiles = (int)(a.B * p.tiles_per_utt);
     p.n_chunks = a.N / bn; p.n_out = n_out; p.eps = a.eps; p.out_f32 = a.out_f32;
     const int units = a.epilogue == TC_LN ? p.m_tiles : p.m_tiles * p.n_chunks;
-    static const char* const tags[4] = {"gemm_tc_bias_act", "gemm_tc_glu", "gemm_tc_res_act", "gemm_tc_layernorm"};
+    static const char* const tags[6] = {"gemm_tc_bias_act", "gemm_tc_glu", "gemm_tc_res_act", "gemm_tc_layernorm",
+                                        "gemm_tc_glu_dw15_silu", "gemm_tc_res_gelu_dw3_gelu"};
     ProfScope ps(tags[a.epilogue], st, 2.0 * a.B * a.T * (double)a.N * a.K * a.taps,
                  2.0 * a.B * a.T * ((double)a.K + n_out * (a.out_f32 ? 2 : 1) + (a.res ? n_out : 0)) + 2.0 * a.N * a.K * a.taps);
 #define ASRB_TC(BN_, EPI_) return launch_one<BN_, EPI_>(ma, mw, mo, p, units, st)
     if (bn == 256) {
         switch (a.epilogue) {
             case TC_BIAS_ACT: ASRB_TC(256, TC_BIAS_ACT);
-            case TC_GLU: ASRB_TC(256, TC_GLU);
             case TC_RES_ACT: ASRB_TC(256, TC_RES_ACT);
             case TC_LN: ASRB_TC(256, TC_LN);
+            case TC_GLU_DW: ASRB_TC(256, TC_GLU_DW);
+            case TC_RES_ACT_DW: ASRB_TC(256, TC_RES_ACT_DW);
         }
     } else {
         switch (a.epilogue) {
@@ -527,14 +662,16 @@ int launch_gemm_tc(const TcGemmArgs& a, cudaStream_t st) {
 // Test hook: the kernel in isolation (include/asrb200.h).
 extern "C" int asrb_test_gemm_tc(const void* a, const void* w, const float* bias, const void* res, const float* gamma,
                                  const float* beta, void* out, int64_t B, int64_t T, int K, int N, int taps,
-                                 int epilogue, int act, void* stream) {
+                                 int epilogue, int act, const float* dw_w, const float* dw_b, int dw_kw, int dw_act,
+                                 const float* pos, void* stream) {
     using namespace asrb;
     if (!a || !w || !bias || !out) return fail(ASRB_E_ARG, "asrb_test_gemm_tc: NULL tensor");
-    if (epilogue < 0 || epilogue > 3 || (taps != 1 && taps != 3)) return fail(ASRB_E_ARG, "asrb_test_gemm_tc: bad epilogue/taps");
+    if (epilogue < 0 || epilogue > 5 || (taps != 1 && taps != 3)) return fail(ASRB_E_ARG, "asrb_test_gemm_tc: bad epilogue/taps");
     ASRB_TRY(require_sm100());
     TcGemmArgs g{};
     g.A = (const __nv_bfloat16*)a; g.W = (const __nv_bfloat16*)w; g.bias = bias; g.res = (const __nv_bfloat16*)res;
     g.gamma = gamma; g.beta = beta; g.out = out;
     g.B = B; g.T = T; g.K = K; g.N = N; g.taps = taps; g.epilogue = epilogue; g.act = act; g.eps = 1e-5f;
+    g.dw_w = dw_w; g.dw_b = dw_b; g.dw_kw = dw_kw; g.dw_act = dw_act; g.pos = pos;
     return launch_gemm_tc(g, (cudaStream_t)stream);
 }

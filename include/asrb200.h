@@ -165,12 +165,17 @@ int asrb_profile_get(int index, const char** tag, float* ms, double* flops, doub
 /* The tcgen05/TMEM/TMA implicit-GEMM in isolation:
  *   out[b,t,:] = epilogue( sum_{tap,k} a[b, t+tap-taps/2, k] * w[n][tap*K + k] + bias[n] )
  * a [B][T][K] bf16, w [N][taps*K] bf16, out [B][T][N or N/2] bf16, res (or NULL) like out.
- * epilogue: 0 bias+act | 1 GLU (w rows interleaved [128 value | 128 gate] per 256) |
- *           2 bias+res+act | 3 bias(+res)+LayerNorm(gamma, beta, eps=1e-5).
- * act: 0 none | 1 GELU | 2 ReLU | 3 SiLU | 4 GELU(GELU).  K % 64 == 0, N % 128 == 0. */
+ * epilogue: 0 bias+act | (1 reserved) |
+ *           2 bias+res+act | 3 bias(+res)+LayerNorm(gamma, beta, eps=1e-5) |
+ *           4 GLU (w rows interleaved [128 value | 128 gate] per 256) -> depthwise(dw_w [kw][N/2], dw_b)
+ *             down the frames -> dw_act |
+ *           5 bias+res+act -> depthwise(dw_w [kw][N], dw_b) -> dw_act (+ pos [T][N]).
+ * act / dw_act: 0 none | 1 GELU | 2 ReLU | 3 SiLU | 4 GELU(GELU).  K % 64 == 0, N % 128 == 0
+ * (N % 256 == 0 for 1, 4, 5); kw in {3, 15}. */
 int asrb_test_gemm_tc(const void* a, const void* w, const float* bias, const void* res,
                       const float* gamma, const float* beta, void* out,
                       int64_t B, int64_t T, int K, int N, int taps, int epilogue, int act,
+                      const float* dw_w, const float* dw_b, int dw_kw, int dw_act, const float* pos,
                       void* stream);
 
 #ifdef __cplusplus

@@ -7,7 +7,17 @@ import torch.nn.functional as F
 pytestmark = pytest.mark.gpu
 
 
-def _ref(a, w, bias, res, gamma, beta, taps, epi, act, N):
+ACTS = {0: lambda x: x, 1: F.gelu, 2: F.relu, 3: F.silu, 4: lambda x: F.gelu(F.gelu(x))}
+
+
+def _depthwise(x, dw_w, dw_b, kw):
+    """x [B, T, C], dw_w [kw][C]: zero-padded depthwise conv along T (per utterance)."""
+    C = x.shape[-1]
+    y = F.conv1d(x.transpose(1, 2), dw_w.t().reshape(C, 1, kw).contiguous(), dw_b, padding=kw // 2, groups=C)
+    return y.transpose(1, 2)
+
+
+def _ref(a, w, bias, res, gamma, beta, taps, epi, act, N, dw=None):
     B, T, K = a.shape
     af = a.float()
     wf = w.float().view(N, taps, K)
@@ -23,14 +33,22 @@ def _ref(a, w, bias, res, gamma, beta, taps, epi, act, N):
             src = af
         acc += src @ wf[:, tap].t()
     acc = acc + bias
-    if epi == 1:                                    # GLU with [128 value | 128 gate] per 256 rows
+    if epi in (1, 4):                               # GLU with [128 value | 128 gate] per 256 rows
         v = acc.view(B, T, N // 256, 2, 128)
-        return (v[..., 0, :] * torch.sigmoid(v[..., 1, :])).reshape(B, T, N // 2)
+        g = (v[..., 0, :] * torch.sigmoid(v[..., 1, :])).reshape(B, T, N // 2)
+        if epi == 1:
+            return g
+        dw_w, dw_b, kw, act2, pos = dw
+        return ACTS[act2](_depthwise(g, dw_w, dw_b, kw))
     if res is not None:
         acc = acc + res.float()
     if epi == 3:
         return F.layer_norm(acc, (N,), gamma, beta, 1e-5)
-    return {0: lambda x: x, 1: F.gelu, 2: F.relu, 3: F.silu, 4: lambda x: F.gelu(F.gelu(x))}[act](acc)
+    if epi == 5:
+        dw_w, dw_b, kw, act2, pos = dw
+        y = ACTS[act2](_depthwise(ACTS[act](acc), dw_w, dw_b, kw))
+        return y + pos if pos is not None else y
+    return ACTS[act](acc)
 
 
 CASES = [
@@ -44,11 +62,15 @@ CASES = [
     (1, 129, 128, 128, 1, 3, 0),        # LN, one 128 chunk, double-buffered accumulators
     (2, 260, 256, 384, 1, 3, 0),        # LN over 3 chunks of 128
     (2, 260, 256, 256, 1, 3, 0),
-    (2, 500, 512, 1024, 1, 1, 0),       # GLU
     (2, 500, 512, 512, 1, 2, 1),        # residual + GELU
     (1, 4000, 2048, 512, 1, 3, 0),      # FFN2 + residual + LN
     (1, 777, 512, 2048, 1, 0, 2),       # FFN1 + ReLU
     (40, 130, 256, 256, 3, 0, 4),       # many small utterances, persistent loop wraps
+    (2, 300, 256, 512, 1, 4, 0),        # GLU -> depthwise-15 -> SiLU (tiles overlap by 14 frames)
+    (3, 115, 512, 1024, 1, 4, 0),
+    (2, 300, 256, 256, 1, 5, 1),        # residual + GELU -> depthwise-3 -> GELU(GELU)
+    (2, 127, 512, 512, 1, 5, 1),
+    (5, 1001, 512, 512, 1, 5, 1),
 ]
 
 
@@ -59,16 +81,26 @@ def test_gemm_tc_matches_torch(built_lib, B, T, K, N, taps, epi, act):
     a = (torch.randn(B, T, K, device="cuda", generator=g) * 0.5).bfloat16()
     w = (torch.randn(N, taps * K, device="cuda", generator=g) / (taps * K) ** 0.5).bfloat16()
     bias = torch.randn(N, device="cuda", generator=g) * 0.1
-    n_out = N // 2 if epi == 1 else N
-    res = (torch.randn(B, T, n_out, device="cuda", generator=g)).bfloat16() if epi in (2, 3) and (T % 2 == 0 or epi == 2) else None
+    n_out = N // 2 if epi in (1, 4) else N
+    res = (torch.randn(B, T, n_out, device="cuda", generator=g)).bfloat16() if epi in (2, 3, 5) and (T % 2 == 0 or epi != 3) else None
     gamma = 1 + 0.2 * torch.randn(N, device="cuda", generator=g)
     beta = 0.1 * torch.randn(N, device="cuda", generator=g)
+    dw = None
+    dw_args = (None, None, 0, 0, None)
+    if epi in (4, 5):
+        kw = 15 if epi == 4 else 3
+        dw_w = torch.randn(kw, n_out, device="cuda", generator=g) / kw ** 0.5
+        dw_b = 0.1 * torch.randn(n_out, device="cuda", generator=g)
+        act2 = 3 if epi == 4 else (4 if T % 2 else 1)
+        pos = torch.randn(T, n_out, device="cuda", generator=g) if (epi == 5 and T % 2 == 0) else None
+        dw = (dw_w, dw_b, kw, act2, pos)
+        dw_args = (dw_w.data_ptr(), dw_b.data_ptr(), kw, act2, pos.data_ptr() if pos is not None else None)
     out = torch.full((B, T, n_out), float("nan"), device="cuda", dtype=torch.bfloat16)
     rc = lib.asrb_test_gemm_tc(a.data_ptr(), w.data_ptr(), bias.data_ptr(), res.data_ptr() if res is not None else None,
-                               gamma.data_ptr(), beta.data_ptr(), out.data_ptr(), B, T, K, N, taps, epi, act, None)
+                               gamma.data_ptr(), beta.data_ptr(), out.data_ptr(), B, T, K, N, taps, epi, act, *dw_args, None)
     built_lib.check(rc, "asrb_test_gemm_tc")
     torch.cuda.synchronize()
-    ref = _ref(a, w, bias, res, gamma, beta, taps, epi, act, N)
+    ref = _ref(a, w, bias, res, gamma, beta, taps, epi, act, N, dw)
     assert not torch.isnan(out.float()).any(), "rows were left unwritten"
     err = (out.float() - ref).abs()
     tol = 2e-2 + 1e-2 * ref.abs()                      # bf16 store rounding dominates

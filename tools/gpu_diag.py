@@ -46,19 +46,32 @@ def gemm(B, T, K, N, taps, epi, act):
     a = (torch.randn(B, T, K, device="cuda", generator=gen) * 0.5).bfloat16()
     w = (torch.randn(N, taps * K, device="cuda", generator=gen) / (taps * K) ** 0.5).bfloat16()
     bias = torch.randn(N, device="cuda", generator=gen) * 0.1
-    n_out = N // 2 if epi == 1 else N
-    res = torch.randn(B, T, n_out, device="cuda", generator=gen).bfloat16() if epi in (2, 3) else None
+    n_out = N // 2 if epi in (1, 4) else N
+    res = torch.randn(B, T, n_out, device="cuda", generator=gen).bfloat16() if epi in (2, 3, 5) else None
     gamma = 1 + 0.2 * torch.randn(N, device="cuda", generator=gen)
     beta = 0.1 * torch.randn(N, device="cuda", generator=gen)
+    dw, dw_args = None, (None, None, 0, 0, None)
+    if epi in (4, 5):
+        kw = 15 if epi == 4 else 3
+        dw_w = torch.randn(kw, n_out, device="cuda", generator=gen) / kw ** 0.5
+        dw_b = 0.1 * torch.randn(n_out, device="cuda", generator=gen)
+        pos = torch.randn(T, n_out, device="cuda", generator=gen) if epi == 5 else None
+        dw = (dw_w, dw_b, kw, 3 if epi == 4 else 4, pos)
+        dw_args = (dw_w.data_ptr(), dw_b.data_ptr(), kw, dw[3], pos.data_ptr() if pos is not None else None)
     out = torch.full((B, T, n_out), float("nan"), device="cuda", dtype=torch.bfloat16)
     rc = lib.asrb_test_gemm_tc(a.data_ptr(), w.data_ptr(), bias.data_ptr(), res.data_ptr() if res is not None else None,
-                               gamma.data_ptr(), beta.data_ptr(), out.data_ptr(), B, T, K, N, taps, epi, act, None)
+                               gamma.data_ptr(), beta.data_ptr(), out.data_ptr(), B, T, K, N, taps, epi, act, *dw_args, None)
     _lib.check(rc, "gemm")
     torch.cuda.synchronize()
-    ref = _ref(a, w, bias, res, gamma, beta, taps, epi, act, N)
+    ref = _ref(a, w, bias, res, gamma, beta, taps, epi, act, N, dw)
     err = (out.float() - ref).abs()
     nan = int(torch.isnan(out.float()).sum())
-    return f"max {float(err.nan_to_num(9e9).max()):.4g} mean {float(err.nan_to_num(0).mean()):.3g} nan {nan} refmax {float(ref.abs().max()):.3g}"
+    bad = (err > 2e-2 + 1e-2 * ref.abs()) | torch.isnan(out.float())
+    where = ""
+    if bool(bad.any()):
+        idx = bad.nonzero()
+        where = f" bad {int(bad.sum())} first {idx[0].tolist()} last {idx[-1].tolist()} rows {sorted(set(idx[:, 1].tolist()))[:12]}"
+    return f"max {float(err.nan_to_num(9e9).max()):.4g} mean {float(err.nan_to_num(0).mean()):.3g} nan {nan} refmax {float(ref.abs().max()):.3g}{where}"
 
 
 for c in CASES if SECTION in ("all", "gemm") else ():
