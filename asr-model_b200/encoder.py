@@ -158,7 +158,7 @@ class AudioEncoder(nn.Module):
         return self._process_feature(x)
 
     def forward_pcm(self, wave: torch.Tensor, frontend, lengths: Optional[torch.Tensor] = None,
-                    return_logmel: bool = False):
+                    return_logmel: bool = False, out: Optional[torch.Tensor] = None):
         """Fused hot path: PCM ``[B, N]`` -> hidden states ``[B, T, dims]`` in one library call
         (``asrb_pcm_to_hidden``).  ``frontend`` is a ``LogMel`` plan with ``n_mels == mels``."""
         if self.training:
@@ -173,7 +173,10 @@ class AudioEncoder(nn.Module):
         B, N = wave.shape
         T = frontend.num_frames(N)
         h = self._handle(wave.device)
-        out = torch.empty(B, T, self.dims, device=wave.device, dtype=self.out_dtype)
+        if out is None:
+            out = torch.empty(B, T, self.dims, device=wave.device, dtype=self.out_dtype)
+        elif tuple(out.shape) != (B, T, self.dims) or out.dtype != self.out_dtype or not out.is_contiguous():
+            raise ValueError("out must be a contiguous [B, T, dims] tensor of the module's out_dtype")
         mel = torch.empty(B, self.mels, T, device=wave.device, dtype=torch.float32) if return_logmel else None
         if lengths is not None:
             lengths = lengths.to(wave.device, torch.int32).contiguous()

@@ -57,17 +57,28 @@ def gather_outputs(local: torch.Tensor, total: int, group=None, out: Optional[to
 
 
 class ShardedEncoder:
-    """Runs ``compute(wave_shard) -> [n, T, D]`` on this rank's utterances and gathers.
+    """Runs ``compute(wave_shard[, out=]) -> [n, T, D]`` on this rank's utterances and gathers.
 
     ``compute`` is the fused hot path (``AudioEncoder.forward_pcm`` bound to a ``LogMel`` plan) in
     production and any shape-preserving function in the gloo CPU tests.  With ``micro`` > 0 the
-    shard is processed in micro-batches; equal-sized micro-batches across ranks are gathered
-    asynchronously while the next one computes.
+    shard is processed in micro-batches.  For equal shards every micro-batch is computed straight
+    into its slot of the gathered ``[total, T, D]`` tensor and exchanged with grouped point-to-point
+    sends/receives (one NCCL group per micro-batch, no staging copies) while the next micro-batch
+    computes; ragged shards fall back to a padded all-gather.
     """
 
-    def __init__(self, compute: Callable[[torch.Tensor], torch.Tensor], group=None, micro: int = 0,
-                 gather: bool = True):
-        self.compute, self.group, self.micro, self.gather = compute, group, micro, gather
+    def __init__(self, compute: Callable[..., torch.Tensor], group=None, micro: int = 0, gather: bool = True,
+                 shape_of: Optional[Callable[[torch.Tensor], Tuple[int, int, torch.dtype]]] = None):
+        self.compute, self.group, self.micro, self.gather, self.shape_of = compute, group, micro, gather, shape_of
+
+    def _run(self, waves, out=None):
+        if out is not None and self.shape_of is not None:
+            return self.compute(waves, out=out)
+        y = self.compute(waves)
+        if out is not None:
+            out.copy_(y)
+            return out
+        return y
 
     def __call__(self, waves: torch.Tensor, total: Optional[int] = None) -> torch.Tensor:
         """``waves`` holds THIS rank's utterances ``[n_r, N]`` (already resident on the rank's
@@ -80,34 +91,33 @@ class ShardedEncoder:
         lo, hi = shard_range(total, rank, world)
         assert hi - lo == n_local, f"rank {rank} holds {n_local} utterances, partition says {hi - lo}"
         if world == 1 or not self.gather:
-            outs = [self.compute(waves[s:e]) for s, e in micro_batches(0, n_local, self.micro)]
+            outs = [self._run(waves[s:e]) for s, e in micro_batches(0, n_local, self.micro)]
             return outs[0] if len(outs) == 1 else torch.cat(outs)
-        equal = total % world == 0 and (self.micro <= 0 or n_local % self.micro == 0)
-        if not equal:
-            local = torch.cat([self.compute(waves[s:e]) for s, e in micro_batches(0, n_local, self.micro)])
+        if total % world != 0:
+            local = torch.cat([self._run(waves[s:e]) for s, e in micro_batches(0, n_local, self.micro)])
             return gather_outputs(local, total, self.group)[0]
-        # pipelined: micro-batch m of every rank lands at out[r*n_local + m*micro ...]
         out = None
-        works = []
-        mb = self.micro if self.micro > 0 else n_local
-        stage = None
-        for s, e in micro_batches(0, n_local, mb):
-            y = self.compute(waves[s:e])
+        pending = []
+        for s, e in micro_batches(0, n_local, self.micro):
             if out is None:
-                out = torch.empty(total, y.shape[1], y.shape[2], dtype=y.dtype, device=y.device)
-                stage = torch.empty(world, mb, y.shape[1], y.shape[2], dtype=y.dtype, device=y.device) \
-                    if mb != n_local else None
-            if stage is None:                       # one micro-batch == the whole shard: in place
-                out[lo:hi].copy_(y)
-                works.append((dist.all_gather_into_tensor(out.view(-1), out[lo:hi].reshape(-1), group=self.group,
-                                                          async_op=True), None, None))
+                if self.shape_of is not None:
+                    T, D, dt = self.shape_of(waves)
+                    out = torch.empty(total, T, D, dtype=dt, device=waves.device)
+                    self._run(waves[s:e], out=out[lo + s: lo + e])
+                else:
+                    y = self.compute(waves[s:e])
+                    out = torch.empty(total, y.shape[1], y.shape[2], dtype=y.dtype, device=y.device)
+                    out[lo + s: lo + e].copy_(y)
             else:
-                buf = torch.empty_like(stage)
-                w = dist.all_gather_into_tensor(buf.view(-1), y.reshape(-1), group=self.group, async_op=True)
-                works.append((w, buf, s))
-        for w, buf, s in works:
+                self._run(waves[s:e], out=out[lo + s: lo + e])
+            ops = []
+            for r in range(world):                      # every peer's slice of this micro-batch lands in place
+                if r == rank:
+                    continue
+                peer = dist.get_global_rank(self.group, r) if self.group is not None else r
+                ops.append(dist.P2POp(dist.isend, out[lo + s: lo + e], peer, self.group))
+                ops.append(dist.P2POp(dist.irecv, out[r * n_local + s: r * n_local + e], peer, self.group))
+            pending.extend(dist.batch_isend_irecv(ops))
+        for w in pending:
             w.wait()
-            if buf is not None:
-                for r in range(world):
-                    out[r * n_local + s: r * n_local + s + mb].copy_(buf[r])
         return out

@@ -177,10 +177,11 @@ def main():
     pcm_host = synth.white_noise_batch(B, N, seed=1234 + rank).pin_memory()
     pcm = pcm_host.to(dev)
 
-    def hot(w):
-        return enc.forward_pcm(w, fe)
+    def hot(w, out=None):
+        return enc.forward_pcm(w, fe, out=out)
 
-    sharded = ShardedEncoder(hot, micro=args.micro if world > 1 else 0, gather=world > 1)
+    sharded = ShardedEncoder(hot, micro=args.micro if world > 1 else 0, gather=world > 1,
+                             shape_of=lambda w: (fe.num_frames(w.shape[1]), DIMS, torch.bfloat16))
 
     def step_resident():
         return sharded(pcm, total=B * world)
