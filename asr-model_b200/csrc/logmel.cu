@@ -44,14 +44,28 @@ struct LogmelCfg {
     static_assert(FB * NB <= GROUPS * YSTRIDE * 2, "power spectra must fit over the FFT buffer");
 };
 
+// cp.async with zero fill: copies `bytes` (0..size) from src and zero-fills the rest of `size`
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src, int bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Persistent: gridDim.x blocks walk the (utterance, frame-tile) list; constants are staged once
+// per block and the PCM span of the NEXT tile streams in with cp.async (zero fill outside
+// [0, len) = the center=True padding) while the current tile is transformed.
 template <int NFFT, int R, int FB>
 __global__ void __launch_bounds__(LogmelCfg<NFFT, R, FB>::THREADS)
-logmel_kernel(const LogmelParams p) {
+logmel_kernel(const LogmelParams p, int tiles_per_utt, int total_tiles) {
     using C = LogmelCfg<NFFT, R, FB>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int span = (FB - 1) * p.hop + NFFT;
-    float*  s_pcm = reinterpret_cast<float*>(smem_raw);                 // [span]
-    float*  s_win = s_pcm + ((span + 3) & ~3);                          // [NFFT]
+    const int span4 = (span + 3) & ~3;
+    float*  s_pcm0 = reinterpret_cast<float*>(smem_raw);                // [2][span4]
+    float*  s_win = s_pcm0 + 2 * span4;                                 // [NFFT]
     float2* s_tw  = reinterpret_cast<float2*>(s_win + NFFT);            // [R*R]
     float2* s_y   = s_tw + R * R;                                       // [GROUPS][YSTRIDE]
     float*  s_pow = reinterpret_cast<float*>(s_y);                      // aliases s_y: [FB][NB]
@@ -61,134 +75,143 @@ logmel_kernel(const LogmelParams p) {
     __shared__ float s_red[32];
 
     const int tid = threadIdx.x;
-    const int b = blockIdx.y;
-    const int t0 = blockIdx.x * FB;
-    const int64_t len = p.lengths ? (int64_t)p.lengths[b] : p.n_samples;
-    const int Tb = 1 + (int)(len / p.hop);                  // valid frames of this utterance
+    const bool vec_ok = ((p.stride & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.pcm) & 15) == 0) && ((p.hop & 3) == 0);
 
-    // ---- stage constants and the PCM span (zero outside [0, len): center=True padding) ----
+    auto prefetch = [&](int tile, float* dstbuf) {       // async copy of one tile's PCM span
+        const int b = tile / tiles_per_utt, t0 = (tile - b * tiles_per_utt) * FB;
+        const int64_t len = p.lengths ? (int64_t)p.lengths[b] : p.n_samples;
+        const float* src = p.pcm + (int64_t)b * p.stride;
+        const int64_t s0 = (int64_t)t0 * p.hop - NFFT / 2;
+        const uint32_t d0 = (uint32_t)__cvta_generic_to_shared(dstbuf);
+        if (vec_ok) {                                     // s0 is a multiple of 4 here
+            for (int i = tid * 4; i < span4; i += C::THREADS * 4) {
+                const int64_t sidx = s0 + i;
+                int64_t valid = len - sidx;               // samples available from sidx
+                valid = valid < 0 ? 0 : (valid > 4 ? 4 : valid);
+                const bool in = sidx >= 0 && valid > 0;   // sidx < 0: whole chunk is padding (sidx multiple of 4)
+                cp_async16(d0 + 4u * i, in ? (const void*)(src + sidx) : (const void*)src, in ? (int)valid * 4 : 0);
+            }
+        } else {
+            for (int i = tid; i < span4; i += C::THREADS) {
+                const int64_t sidx = s0 + i;
+                const bool in = sidx >= 0 && sidx < len;
+                cp_async4(d0 + 4u * i, in ? (const void*)(src + sidx) : (const void*)p.pcm, in ? 4 : 0);
+            }
+        }
+        cp_async_commit();
+    };
+
+    int tile = blockIdx.x;
+    if (tile < total_tiles) prefetch(tile, s_pcm0);
+    // ---- constants, once per block ----
     for (int i = tid; i < NFFT; i += C::THREADS) s_win[i] = p.window[i];
     for (int i = tid; i < R * R; i += C::THREADS) s_tw[i] = p.twiddle[i];
     for (int i = tid; i < p.M * p.kmax; i += C::THREADS) s_melw[i] = p.mel_w[i];
     for (int i = tid; i < p.M; i += C::THREADS) { s_lo[i] = p.mel_lo[i]; s_cnt[i] = p.mel_cnt[i]; }
-    {
-        const float* src = p.pcm + (int64_t)b * p.stride;
-        const int64_t s0 = (int64_t)t0 * p.hop - NFFT / 2;
-        const bool vec_ok = ((p.stride & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.pcm) & 15) == 0) &&
-                            ((p.hop & 3) == 0);
-        if (vec_ok) {                                       // s0 is a multiple of 4 here
-            for (int i = tid * 4; i < span; i += C::THREADS * 4) {
-                int64_t s = s0 + i;
-                float4 v;
-                if (s >= 0 && s + 3 < len) {
-                    v = __ldg(reinterpret_cast<const float4*>(src + s));
-                } else {
-                    v.x = (s >= 0 && s < len) ? src[s] : 0.f;
-                    v.y = (s + 1 >= 0 && s + 1 < len) ? src[s + 1] : 0.f;
-                    v.z = (s + 2 >= 0 && s + 2 < len) ? src[s + 2] : 0.f;
-                    v.w = (s + 3 >= 0 && s + 3 < len) ? src[s + 3] : 0.f;
-                }
-                *reinterpret_cast<float4*>(s_pcm + i) = v;  // span rounded up to 4 in smem
-            }
-        } else {
-            for (int i = tid; i < span; i += C::THREADS) {
-                int64_t s = s0 + i;
-                s_pcm[i] = (s >= 0 && s < len) ? src[s] : 0.f;
-            }
-        }
-    }
-    __syncthreads();
 
     const int g = tid / R, j = tid - g * R;
     float2* yg = s_y + g * C::YSTRIDE;
-
-    // ---- round 1: R-point DFT over n1 of z[R n1 + j], twiddle W_N^(j k1), transpose ----
-    {
-        float2 x[R];
-        const float* fa = s_pcm + (2 * g) * p.hop;
-        const float* fb = fa + p.hop;
-#pragma unroll
-        for (int n1 = 0; n1 < R; ++n1) {
-            const int n = R * n1 + j;
-            const float w = s_win[n];
-            x[n1] = make_float2(w * fa[n], w * fb[n]);
-        }
-        SmallDFT<R>::run(x);
-        yg[j] = x[0];
-#pragma unroll
-        for (int k1 = 1; k1 < R; ++k1) yg[k1 * (R + 1) + j] = cmul(x[k1], s_tw[k1 * R + j]);
-    }
-    __syncthreads();
-
-    // ---- round 2: thread k1 = j does the R-point DFT over n2 -> Z[j + R k2] ----
-    {
-        float2 y[R];
-#pragma unroll
-        for (int n2 = 0; n2 < R; ++n2) y[n2] = yg[j * (R + 1) + n2];
-        SmallDFT<R>::run(y);
-        __syncthreads();                                    // everyone has read the transpose
-#pragma unroll
-        for (int k2 = 0; k2 < R; ++k2) yg[j + R * k2] = y[k2];
-    }
-    __syncthreads();
-
-    // ---- split the packed pair: A[k] = (Z[k] + conj Z[N-k]) / 2, B[k] = (Z[k] - conj Z[N-k]) / 2i ----
-    float pa[C::BINS_PER_THREAD], pb[C::BINS_PER_THREAD];
-#pragma unroll
-    for (int i = 0; i < C::BINS_PER_THREAD; ++i) {
-        const int k = j + R * i;
-        pa[i] = pb[i] = 0.f;
-        if (k < C::NB) {
-            const float2 z1 = yg[k];
-            const float2 z2 = yg[(NFFT - k) % NFFT];
-            const float ar = z1.x + z2.x, ai = z1.y - z2.y;     // 2 Re A, 2 Im A
-            const float br = z1.y + z2.y, bi = z2.x - z1.x;     // 2 Re B, 2 Im B
-            pa[i] = 0.25f * fmaf(ar, ar, ai * ai);
-            pb[i] = 0.25f * fmaf(br, br, bi * bi);
-        }
-    }
-    __syncthreads();                                        // Z is dead: reuse it for |X|^2
-#pragma unroll
-    for (int i = 0; i < C::BINS_PER_THREAD; ++i) {
-        const int k = j + R * i;
-        if (k < C::NB) {
-            s_pow[(2 * g) * C::NB + k] = pa[i];
-            s_pow[(2 * g + 1) * C::NB + k] = pb[i];
-        }
-    }
-    __syncthreads();
-
-    // ---- banded mel projection + log10 + (x+4)/4; lane -> frame so stores are coalesced ----
+    const int lane = tid & 31, warp = tid >> 5;
+    constexpr int nwarp = C::THREADS / 32;
     constexpr int FW = FB < 32 ? FB : 32;                   // frames handled by one warp pass
     constexpr int MSUB = 32 / FW;                           // filters handled side by side
-    const int lane = tid & 31, warp = tid >> 5;
-    const int nwarp = C::THREADS / 32;
-    const int f = lane % FW;
-    float vmax = -INFINITY;
-    for (int fbase = 0; fbase < FB; fbase += FW) {
-        const int fr = fbase + f;
-        const int t = t0 + fr;
-        const float* pw = s_pow + fr * C::NB;
-        for (int m = warp * MSUB + lane / FW; m < p.M; m += nwarp * MSUB) {
-            const int lo = s_lo[m], cnt = s_cnt[m];
-            const float* w = s_melw + m * p.kmax;
-            float acc = 0.f;
-            for (int i = 0; i < cnt; ++i) acc = fmaf(w[i], pw[lo + i], acc);
-            const float lg = log10f(fmaxf(acc, 1e-10f));                    // essentials.py:488
-            if (t < p.T) {
-                float s = 0.f;                                              // DataCollator pad value
-                if (t < Tb) { vmax = fmaxf(vmax, lg); s = (lg + 4.0f) / 4.0f; }   // essentials.py:490
-                p.out[((int64_t)b * p.M + m) * p.T + t] = s;
+
+    for (int it = 0; tile < total_tiles; tile += gridDim.x, ++it) {
+        float* s_pcm = s_pcm0 + (it & 1) * span4;
+        const int next = tile + gridDim.x;
+        if (next < total_tiles) { prefetch(next, s_pcm0 + ((it + 1) & 1) * span4); cp_async_wait<1>(); }
+        else cp_async_wait<0>();
+        __syncthreads();                                    // this tile's PCM (and the constants) are visible
+
+        const int b = tile / tiles_per_utt, t0 = (tile - b * tiles_per_utt) * FB;
+        const int64_t len = p.lengths ? (int64_t)p.lengths[b] : p.n_samples;
+        const int Tb = 1 + (int)(len / p.hop);              // valid frames of this utterance
+
+        // ---- round 1: R-point DFT over n1 of z[R n1 + j], twiddle W_N^(j k1), transpose ----
+        {
+            float2 x[R];
+            const float* fa = s_pcm + (2 * g) * p.hop;
+            const float* fb = fa + p.hop;
+#pragma unroll
+            for (int n1 = 0; n1 < R; ++n1) {
+                const int n = R * n1 + j;
+                const float w = s_win[n];
+                x[n1] = make_float2(w * fa[n], w * fb[n]);
+            }
+            SmallDFT<R>::run(x);
+            yg[j] = x[0];
+#pragma unroll
+            for (int k1 = 1; k1 < R; ++k1) yg[k1 * (R + 1) + j] = cmul(x[k1], s_tw[k1 * R + j]);
+        }
+        __syncthreads();
+
+        // ---- round 2: thread k1 = j does the R-point DFT over n2 -> Z[j + R k2] ----
+        {
+            float2 y[R];
+#pragma unroll
+            for (int n2 = 0; n2 < R; ++n2) y[n2] = yg[j * (R + 1) + n2];
+            SmallDFT<R>::run(y);
+            __syncthreads();                                // everyone has read the transpose
+#pragma unroll
+            for (int k2 = 0; k2 < R; ++k2) yg[j + R * k2] = y[k2];
+        }
+        __syncthreads();
+
+        // ---- split the packed pair: A[k] = (Z[k] + conj Z[N-k]) / 2, B[k] = (Z[k] - conj Z[N-k]) / 2i ----
+        float pa[C::BINS_PER_THREAD], pb[C::BINS_PER_THREAD];
+#pragma unroll
+        for (int i = 0; i < C::BINS_PER_THREAD; ++i) {
+            const int k = j + R * i;
+            pa[i] = pb[i] = 0.f;
+            if (k < C::NB) {
+                const float2 z1 = yg[k];
+                const float2 z2 = yg[k == 0 ? 0 : NFFT - k];
+                const float ar = z1.x + z2.x, ai = z1.y - z2.y;     // 2 Re A, 2 Im A
+                const float br = z1.y + z2.y, bi = z2.x - z1.x;     // 2 Re B, 2 Im B
+                pa[i] = 0.25f * fmaf(ar, ar, ai * ai);
+                pb[i] = 0.25f * fmaf(br, br, bi * bi);
             }
         }
-    }
-    vmax = warp_max(vmax);
-    if (lane == 0) s_red[warp] = vmax;
-    __syncthreads();
-    if (warp == 0) {
-        float v = lane < nwarp ? s_red[lane] : -INFINITY;
-        v = warp_max(v);
-        if (lane == 0 && v > -INFINITY) atomicMax(p.keys + b, f2key(v));
+        __syncthreads();                                    // Z is dead: reuse it for |X|^2
+#pragma unroll
+        for (int i = 0; i < C::BINS_PER_THREAD; ++i) {
+            const int k = j + R * i;
+            if (k < C::NB) {
+                s_pow[(2 * g) * C::NB + k] = pa[i];
+                s_pow[(2 * g + 1) * C::NB + k] = pb[i];
+            }
+        }
+        __syncthreads();
+
+        // ---- banded mel projection + log10 + (x+4)/4; lane -> frame so stores are coalesced ----
+        const int f = lane % FW;
+        float vmax = -INFINITY;
+        for (int fbase = 0; fbase < FB; fbase += FW) {
+            const int fr = fbase + f;
+            const int t = t0 + fr;
+            const float* pw = s_pow + fr * C::NB;
+            for (int m = warp * MSUB + lane / FW; m < p.M; m += nwarp * MSUB) {
+                const int lo = s_lo[m], cnt = s_cnt[m];
+                const float* w = s_melw + m * p.kmax;
+                float acc = 0.f;
+                for (int i = 0; i < cnt; ++i) acc = fmaf(w[i], pw[lo + i], acc);
+                // log10 through MUFU lg2 (abs error ~2^-22 in log2: 7e-8 in log10)   essentials.py:488
+                const float lg = __log2f(fmaxf(acc, 1e-10f)) * 0.30102999566398120f;
+                if (t < p.T) {
+                    float sv = 0.f;                                         // DataCollator pad value
+                    if (t < Tb) { vmax = fmaxf(vmax, lg); sv = (lg + 4.0f) / 4.0f; }   // essentials.py:490
+                    p.out[((int64_t)b * p.M + m) * p.T + t] = sv;
+                }
+            }
+        }
+        vmax = warp_max(vmax);
+        if (lane == 0) s_red[warp] = vmax;
+        __syncthreads();                                    // also: s_pow / s_pcm are free for the next tile
+        if (warp == 0) {
+            float v = lane < nwarp ? s_red[lane] : -INFINITY;
+            v = warp_max(v);
+            if (lane == 0 && v > -INFINITY) atomicMax(p.keys + b, f2key(v));
+        }
     }
 }
 
@@ -285,13 +308,20 @@ template <int NFFT, int R, int FB>
 static int launch_logmel(const asrb_logmel_plan* pl, LogmelParams p, int64_t batch, cudaStream_t st) {
     using C = LogmelCfg<NFFT, R, FB>;
     const int span = (FB - 1) * pl->hop + NFFT;
-    size_t smem = sizeof(float) * (((span + 3) & ~3) + NFFT) + sizeof(float2) * (R * R + C::GROUPS * C::YSTRIDE) +
+    size_t smem = sizeof(float) * (2 * ((span + 3) & ~3) + NFFT) + sizeof(float2) * (R * R + C::GROUPS * C::YSTRIDE) +
                   sizeof(float) * (size_t)pl->n_mels * pl->kmax + sizeof(int) * 2 * pl->n_mels;
     if (smem > 227 * 1024) return fail(ASRB_E_ARG, "asrb_logmel_f32: hop/n_mels need %zu B of shared memory", smem);
     auto kern = logmel_kernel<NFFT, R, FB>;
     ASRB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid((p.T + FB - 1) / FB, (unsigned)batch);
-    kern<<<grid, C::THREADS, smem, st>>>(p);
+    int per_sm = 1;
+    ASRB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, C::THREADS, smem));
+    if (per_sm < 1) per_sm = 1;
+    const int tiles_per_utt = (p.T + FB - 1) / FB;
+    const int64_t total = (int64_t)tiles_per_utt * batch;
+    if (total > 0x7fffffff) return fail(ASRB_E_ARG, "asrb_logmel_f32: too many frame tiles");
+    int grid = sm_count() * per_sm;
+    if (grid > total) grid = (int)total;
+    kern<<<grid, C::THREADS, smem, st>>>(p, tiles_per_utt, (int)total);
     ASRB_LAUNCH_CHECK();
     return ASRB_OK;
 }
