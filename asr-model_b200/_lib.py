@@ -49,6 +49,7 @@ SYMBOLS = {
     "asrb_profile_end": (_int, []),
     "asrb_profile_get": (_int, [_int, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.POINTER(C.c_double),
                                 C.POINTER(C.c_double)]),
+    "asrb_test_attention_tc": (_int, [_vp, _vp, _i64, _i64, _int, _int, _vp]),
     "asrb_test_gemm_tc": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _int, _int, _int, _int, _int,
                                  _vp, _vp, _int, _int, _vp, _vp]),
 }

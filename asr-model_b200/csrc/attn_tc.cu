@@ -1,0 +1,308 @@
+// Flash-style softmax attention on tcgen05 / TMEM for the optional TransformerEncoderLayer
+// (model.py:138,163: nn.MultiheadAttention, no mask, non-causal, softmax(q k^T / sqrt(hd)) v).
+//
+// One CTA = one (utterance, head, 128-query tile).  qkv is the packed bf16 [B][T][3D] output of
+// the in_proj GEMM; Q, K and V tiles arrive by TMA (3-D map, OOB rows zero filled).
+//   warp 0      TMA producer: Q once, then a 2-deep ring of K tiles and a 2-deep ring of V tiles
+//   warp 1      MMA issuer:   S_j = Q K_j^T (SS, both K-major)  ->  TMEM S[j&1] (128 fp32 columns)
+//                             O  += P_j V_j (A = P in smem K-major, B = V in smem MN-major) -> TMEM O
+//   warps 2..5  softmax:      thread = query row (TMEM lane); online softmax in the exp2 domain with
+//                             a stale running max (O is rescaled in TMEM only when the max grew by
+//                             more than 2^8), P_j -> bf16 -> swizzled smem, final O / l -> out bf16.
+// S is never written to HBM; scores and probabilities live in TMEM / shared memory only.
+#include "tc_common.cuh"
+
+namespace asrb {
+
+template <int HD> struct AttnCfg {
+    static constexpr int SUB = HD / 64;                          // 64-column sub-tiles per head_dim
+    static constexpr int Q_BYTES = BM * HD * 2;
+    static constexpr int KV_BYTES = BM * HD * 2;                 // one K (or V) tile: 128 keys x HD
+    static constexpr int P_BYTES = BM * BM * 2;                  // 128 queries x 128 keys bf16
+    static constexpr int SMEM = Q_BYTES + 4 * KV_BYTES + 2 * P_BYTES + 256;
+    static constexpr int THREADS = 192;
+    static_assert(SMEM <= 227 * 1024, "shared memory budget");
+};
+
+struct AttnParams { int T, D, H, n_kv; float scale_log2; __nv_bfloat16* out; };
+
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) {
+    const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+          "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+          "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+          "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31]) : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
+// MN-major, SWIZZLE_128B B operand (V tile: rows = keys (K), 64 head-dim columns (N) per 128-byte row):
+// 8-key groups 1024 B apart (SBO), the next 64 columns of N one sub-tile (16 KB) further (LBO).
+__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t saddr, uint32_t lbo_bytes) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | (64ull << 32) |
+           (1ull << 46) | (2ull << 61);
+}
+__host__ __device__ constexpr uint32_t make_idesc_ex(int n, bool b_mn_major) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((b_mn_major ? 1u : 0u) << 16) | ((uint32_t)(n >> 3) << 17) |
+           ((uint32_t)(BM >> 4) << 24);
+}
+__device__ __forceinline__ float ex2f(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+template <int HD>
+__global__ void __launch_bounds__(AttnCfg<HD>::THREADS, 1)
+attn_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParams p) {
+    using C = AttnCfg<HD>;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    unsigned char* s_q = smem;                                   // [SUB][128][128 B]
+    unsigned char* s_k = s_q + C::Q_BYTES;                       // [2][SUB][128][128 B]
+    unsigned char* s_v = s_k + 2 * C::KV_BYTES;                  // [2][SUB][128][128 B]
+    unsigned char* s_p = s_v + 2 * C::KV_BYTES;                  // [2][2][128][128 B]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_p + 2 * C::P_BYTES);
+    const uint32_t bar0 = smem_u32(bars);
+    // q_full, k_full[2], k_empty[2], v_full[2], v_empty[2], s_full[2], p_ready[2], pv_done[2]
+    const uint32_t q_full = bar0;
+    auto k_full = [&](int s) { return bar0 + 8u * (1 + s); };
+    auto k_empty = [&](int s) { return bar0 + 8u * (3 + s); };
+    auto v_full = [&](int s) { return bar0 + 8u * (5 + s); };
+    auto v_empty = [&](int s) { return bar0 + 8u * (7 + s); };
+    auto s_full = [&](int s) { return bar0 + 8u * (9 + s); };
+    auto p_ready = [&](int s) { return bar0 + 8u * (11 + s); };
+    auto pv_done = [&](int s) { return bar0 + 8u * (13 + s); };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * BM, h = blockIdx.y, b = blockIdx.z;
+    const int n_kv = p.n_kv;
+
+    if (warp == 0 && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_qkv) : "memory");
+    if (warp == 1 && lane == 0) {
+        mbar_init(q_full, 1);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(k_full(s), 1); mbar_init(k_empty(s), 1); mbar_init(v_full(s), 1); mbar_init(v_empty(s), 1);
+            mbar_init(s_full(s), 1); mbar_init(p_ready(s), 128); mbar_init(pv_done(s), 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tm_s = tmem_base;                 // S[2]: columns [0, 256)
+    const uint32_t tm_o = tmem_base + 256;           // O: columns [256, 256 + HD)
+
+    if (warp == 0) {
+        // ================================ TMA producer ================================
+        if (lane == 0) {
+            mbar_expect_tx(q_full, C::Q_BYTES);
+            for (int s = 0; s < C::SUB; ++s)
+                tma_load_3d(smem_u32(s_q + s * (BM * 128)), &map_qkv, h * HD + s * 64, q0, b, q_full);
+            for (int j = 0; j < n_kv; ++j) {
+                const int st = j & 1; const uint32_t ph = (uint32_t)(j >> 1) & 1u;
+                mbar_wait(k_empty(st), ph ^ 1);
+                mbar_expect_tx(k_full(st), C::KV_BYTES);
+                for (int s = 0; s < C::SUB; ++s)
+                    tma_load_3d(smem_u32(s_k + st * C::KV_BYTES + s * (BM * 128)), &map_qkv, p.D + h * HD + s * 64, j * BM, b, k_full(st));
+                mbar_wait(v_empty(st), ph ^ 1);
+                mbar_expect_tx(v_full(st), C::KV_BYTES);
+                for (int s = 0; s < C::SUB; ++s)
+                    tma_load_3d(smem_u32(s_v + st * C::KV_BYTES + s * (BM * 128)), &map_qkv, 2 * p.D + h * HD + s * 64, j * BM, b, v_full(st));
+            }
+        }
+    } else if (warp == 1) {
+        // ================================ MMA issuer ==================================
+        if (lane == 0) {
+            constexpr uint32_t idesc_qk = make_idesc_ex(BM, false);        // N = 128 keys
+            constexpr uint32_t idesc_pv = make_idesc_ex(HD, true);         // N = head_dim, B = V is MN-major
+            auto issue_qk = [&](int j) {
+                const int st = j & 1; const uint32_t ph = (uint32_t)(j >> 1) & 1u;
+                mbar_wait(k_full(st), ph);
+                tc_fence_after();
+#pragma unroll
+                for (int kk = 0; kk < HD / 16; ++kk) {
+                    const uint32_t off = (uint32_t)((kk >> 2) * (BM * 128) + (kk & 3) * 32);
+                    tc_mma(tm_s + (uint32_t)(st * BM), make_smem_desc(smem_u32(s_q) + off),
+                           make_smem_desc(smem_u32(s_k + st * C::KV_BYTES) + off), idesc_qk, (uint32_t)(kk != 0));
+                }
+                tc_commit(k_empty(st));
+                tc_commit(s_full(st));
+            };
+            mbar_wait(q_full, 0);
+            tc_fence_after();
+            issue_qk(0);
+            if (n_kv > 1) issue_qk(1);
+            for (int j = 0; j < n_kv; ++j) {
+                const int st = j & 1; const uint32_t ph = (uint32_t)(j >> 1) & 1u;
+                mbar_wait(p_ready(st), ph);                                 // P_j in smem, S[st] free, O rescaled if needed
+                mbar_wait(v_full(st), ph);
+                tc_fence_after();
+#pragma unroll
+                for (int kk = 0; kk < BM / 16; ++kk) {                      // 128 keys = 8 MMAs of K = 16
+                    const uint64_t adesc = make_smem_desc(smem_u32(s_p + st * C::P_BYTES) + (uint32_t)((kk >> 2) * (BM * 128) + (kk & 3) * 32));
+                    const uint64_t bdesc = make_smem_desc_mn(smem_u32(s_v + st * C::KV_BYTES) + (uint32_t)(kk * 16 * 128), BM * 128);
+                    tc_mma(tm_o, adesc, bdesc, idesc_pv, (uint32_t)((j | kk) != 0));
+                }
+                tc_commit(v_empty(st));
+                tc_commit(pv_done(st));
+                if (j + 2 < n_kv) issue_qk(j + 2);
+            }
+        }
+    } else {
+        // ================================ softmax warps ===============================
+        const int quad = warp & 3;
+        const int r = quad * 32 + lane;                              // query row of this thread
+        const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
+        float m_used = -INFINITY;                                    // max the exponents are taken against
+        float l = 0.f;
+        for (int j = 0; j < n_kv; ++j) {
+            const int st = j & 1; const uint32_t ph = (uint32_t)(j >> 1) & 1u;
+            mbar_wait(s_full(st), ph);
+            tc_fence_after();
+            const uint32_t ts = tm_s + lane_off + (uint32_t)(st * BM);
+            const int kbase = j * BM;
+            const bool tail = kbase + BM > p.T;                      // keys >= T are padding: mask them
+            // ---- pass A: row max of the scaled scores ----
+            float mx = -INFINITY;
+#pragma unroll
+            for (int c = 0; c < BM; c += 32) {
+                float v[32];
+                tmem_ld32(ts + c, v);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const float sv = (tail && kbase + c + i >= p.T) ? -INFINITY : v[i] * p.scale_log2;
+                    mx = fmaxf(mx, sv);
+                }
+            }
+            // ---- rescale O only when the max grew by more than 2^8 (warp-uniform decision) ----
+            const bool grow = mx > m_used + 8.0f;
+            if (__any_sync(0xffffffffu, grow)) {
+                const float m_new = grow ? mx : m_used;
+                const float factor = (m_used == -INFINITY) ? 0.f : ex2f(m_used - m_new);
+                if (j > 0) {
+                    mbar_wait(pv_done((j - 1) & 1), (uint32_t)((j - 1) >> 1) & 1u);     // O is quiescent
+                    tc_fence_after();
+#pragma unroll
+                    for (int c = 0; c < HD; c += 32) {
+                        float o[32];
+                        tmem_ld32(tm_o + lane_off + c, o);
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) o[i] *= factor;
+                        tmem_st32(tm_o + lane_off + c, o);
+                    }
+                    tc_fence_before();
+                }
+                l *= factor;
+                m_used = m_new;
+            }
+            // ---- pass B: p = 2^(s - m_used), row sum, P -> bf16 -> swizzled smem (A operand of P V) ----
+            if (j >= 2) mbar_wait(pv_done(st), (uint32_t)((j - 2) >> 1) & 1u);          // P buffer st is free again
+            unsigned char* pbuf = s_p + st * C::P_BYTES;
+#pragma unroll
+            for (int c = 0; c < BM; c += 32) {
+                float v[32];
+                tmem_ld32(ts + c, v);
+                float rs = 0.f;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const float sv = (tail && kbase + c + i >= p.T) ? -INFINITY : v[i] * p.scale_log2;
+                    v[i] = ex2f(sv - m_used);
+                    rs += v[i];
+                }
+                l += rs;
+                unsigned char* sub = pbuf + (c >> 6) * (BM * 128) + r * 128;             // 64-key sub-tile, row r
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int chunk = ((c & 32) >> 3) + i;
+                    uint4 q;
+                    __nv_bfloat162 h0 = __floats2bfloat162_rn(v[8 * i + 0], v[8 * i + 1]), h1 = __floats2bfloat162_rn(v[8 * i + 2], v[8 * i + 3]);
+                    __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * i + 4], v[8 * i + 5]), h3 = __floats2bfloat162_rn(v[8 * i + 6], v[8 * i + 7]);
+                    q.x = *reinterpret_cast<uint32_t*>(&h0); q.y = *reinterpret_cast<uint32_t*>(&h1);
+                    q.z = *reinterpret_cast<uint32_t*>(&h2); q.w = *reinterpret_cast<uint32_t*>(&h3);
+                    *reinterpret_cast<uint4*>(sub + ((chunk ^ (r & 7)) << 4)) = q;
+                }
+            }
+            fence_async_smem();                                      // generic-proxy writes -> visible to the MMA (async proxy)
+            tc_fence_before();
+            mbar_arrive(p_ready(st));
+        }
+        // ---- epilogue: O / l -> bf16 -> out[b, q0 + r, h*HD ...] ----
+        mbar_wait(pv_done((n_kv - 1) & 1), (uint32_t)((n_kv - 1) >> 1) & 1u);
+        tc_fence_after();
+        const float inv = 1.0f / l;
+        const int t = q0 + r;
+#pragma unroll
+        for (int c = 0; c < HD; c += 32) {
+            float o[32];
+            tmem_ld32(tm_o + lane_off + c, o);
+            if (t < p.T) {
+                __nv_bfloat16* dst = p.out + ((int64_t)b * p.T + t) * p.D + h * HD + c;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    uint4 q;
+                    __nv_bfloat162 h0 = __floats2bfloat162_rn(o[8 * i + 0] * inv, o[8 * i + 1] * inv), h1 = __floats2bfloat162_rn(o[8 * i + 2] * inv, o[8 * i + 3] * inv);
+                    __nv_bfloat162 h2 = __floats2bfloat162_rn(o[8 * i + 4] * inv, o[8 * i + 5] * inv), h3 = __floats2bfloat162_rn(o[8 * i + 6] * inv, o[8 * i + 7] * inv);
+                    q.x = *reinterpret_cast<uint32_t*>(&h0); q.y = *reinterpret_cast<uint32_t*>(&h1);
+                    q.z = *reinterpret_cast<uint32_t*>(&h2); q.w = *reinterpret_cast<uint32_t*>(&h3);
+                    *reinterpret_cast<uint4*>(dst + 8 * i) = q;
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
+bool attention_tc_supported(int D, int H) {
+    const int hd = H > 0 ? D / H : 0;
+    return H > 0 && D % H == 0 && (hd == 64 || hd == 128) && (3 * D) % 8 == 0;
+}
+
+template <int HD>
+static int launch_attn(const CUtensorMap& map, const AttnParams& p, int64_t B, cudaStream_t st) {
+    auto kern = attn_tc_kernel<HD>;
+    ASRB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<HD>::SMEM));
+    dim3 grid((unsigned)((p.T + BM - 1) / BM), (unsigned)p.H, (unsigned)B);
+    kern<<<grid, AttnCfg<HD>::THREADS, AttnCfg<HD>::SMEM, st>>>(map, p);
+    ASRB_LAUNCH_CHECK();
+    return ASRB_OK;
+}
+
+// qkv [B][T][3D] bf16 (q | k | v) -> out [B][T][D] bf16, softmax(q k^T * scale) v per head.
+int launch_attention_tc(const void* qkv, void* out, int64_t B, int64_t T, int D, int H, float scale, cudaStream_t st) {
+    if (!attention_tc_supported(D, H)) return fail(ASRB_E_ARG, "tcgen05 attention: head_dim %d unsupported (64 or 128)", H ? D / H : 0);
+    if (B <= 0 || T <= 0) return ASRB_OK;
+    if (B > 65535) return fail(ASRB_E_ARG, "tcgen05 attention: batch %lld > 65535", (long long)B);
+    CUtensorMap map;
+    ASRB_TRY(make_act_map(&map, qkv, B, T, 3 * D));
+    AttnParams p;
+    p.T = (int)T; p.D = D; p.H = H; p.n_kv = (int)((T + BM - 1) / BM);
+    p.scale_log2 = scale * 1.4426950408889634f; p.out = (__nv_bfloat16*)out;
+    ProfScope ps("attention_tc", st, 4.0 * B * (double)T * T * D, 2.0 * B * T * D * 4.0);
+    if (D / H == 128) return launch_attn<128>(map, p, B, st);
+    return launch_attn<64>(map, p, B, st);
+}
+
+}  // namespace asrb
+
+// Test hook (include/asrb200.h)
+extern "C" int asrb_test_attention_tc(const void* qkv, void* out, int64_t B, int64_t T, int D, int H, void* stream) {
+    using namespace asrb;
+    if (!qkv || !out || H <= 0) return fail(ASRB_E_ARG, "asrb_test_attention_tc: bad argument");
+    ASRB_TRY(require_sm100());
+    return launch_attention_tc(qkv, out, B, T, D, H, 1.0f / sqrtf((float)(D / H)), (cudaStream_t)stream);
+}

@@ -47,6 +47,10 @@ int launch_attention_simt_ex(const void* q, const void* k, const void* v, int64_
                              void* out, DType dt, int64_t B, int64_t T, int D, int H, float scale,
                              cudaStream_t st);
 
+// Flash-style attention on tcgen05/TMEM (attn_tc.cu): bf16 qkv [B][T][3D] -> bf16 out [B][T][D]; head_dim 64 | 128
+bool attention_tc_supported(int D, int H);
+int launch_attention_tc(const void* qkv, void* out, int64_t B, int64_t T, int D, int H, float scale, cudaStream_t st);
+
 // RMSNorm rows (nn.RMSNorm, eps = fp32 machine eps): out = x / sqrt(mean(x^2)+eps) * w
 int launch_rmsnorm(const float* x, const float* w, float* out, int64_t rows, int D, cudaStream_t st);
 // rotary (model.py:198-214) + per-head RMSNorm (model.py:307) in place on x [B*T][ld], heads at h*hd

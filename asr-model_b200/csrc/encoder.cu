@@ -365,7 +365,8 @@ int encoder_body(asrb_encoder* e, const EncBuffers& w, const float* x_c1, int in
         q.A = (const __nv_bfloat16*)w.X; q.W = e->win_h; q.bias = e->bin; q.out = w.wide;
         q.B = B; q.T = T; q.K = D; q.N = 3 * D; q.taps = 1; q.epilogue = TC_BIAS_ACT; q.act = ACT_NONE;
         ASRB_TRY(launch_gemm_tc(q, st));
-        ASRB_TRY(launch_attention_simt(w.wide, w.U, DT_BF16, B, T, D, H, scale, st));
+        if (attention_tc_supported(D, H)) ASRB_TRY(launch_attention_tc(w.wide, w.U, B, T, D, H, scale, st));
+        else ASRB_TRY(launch_attention_simt(w.wide, w.U, DT_BF16, B, T, D, H, scale, st));
         const bool fused_ln = tc_gemm_supported(D, D, TC_LN);
         float* x32 = fused_ln ? (float*)w.G : nullptr;       // written by the last depthwise kernel
         float* y32 = fused_ln ? (float*)w.H : nullptr;
@@ -375,8 +376,11 @@ int encoder_body(asrb_encoder* e, const EncBuffers& w, const float* x_c1, int in
         f1.B = B; f1.T = T; f1.K = D; f1.N = F; f1.taps = 1; f1.epilogue = TC_BIAS_ACT; f1.act = ACT_RELU;
         ASRB_TRY(launch_gemm_tc(f1, st));
         ASRB_TRY(tc_gemm_ln((const __nv_bfloat16*)w.ffn, e->wf2_h, e->bf2, (const __nv_bfloat16*)w.Y, e->n2g, e->n2b, fin, w.wide, B, T, F, D, 1, st, y32, nullptr));
-        ProfScope ps("convert", st, 0.0, 6.0 * rows * D);
-        if (!same) { convert_kernel<<<148 * 8, 256, 0, st>>>((const __nv_bfloat16*)fin, (float*)out, rows * D); ASRB_LAUNCH_CHECK(); }
+        if (!same) {
+            ProfScope ps("convert", st, 0.0, 6.0 * rows * D);
+            convert_kernel<<<148 * 8, 256, 0, st>>>((const __nv_bfloat16*)fin, (float*)out, rows * D);
+            ASRB_LAUNCH_CHECK();
+        }
     } else {
         ASRB_TRY(launch_gemm_simt(w.X, DT_F32, e->win_f, e->bin, nullptr, w.wide, DT_F32, B, T, D, 3 * D, 1, ACT_NONE, st));
         ASRB_TRY(launch_attention_simt(w.wide, w.U, DT_F32, B, T, D, H, scale, st));

@@ -178,6 +178,11 @@ int asrb_test_gemm_tc(const void* a, const void* w, const float* bias, const voi
                       const float* dw_w, const float* dw_b, int dw_kw, int dw_act, const float* pos,
                       void* stream);
 
+/* The tcgen05 flash-style attention in isolation: qkv [B][T][3D] bf16 (q | k | v, heads contiguous
+ * inside each) -> out [B][T][D] bf16 = softmax(q k^T / sqrt(D/H)) v per head, no mask (model.py:163).
+ * D/H must be 64 or 128. */
+int asrb_test_attention_tc(const void* qkv, void* out, int64_t B, int64_t T, int D, int H, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
