@@ -28,9 +28,9 @@ template <int BN> struct TcCfg {
     static constexpr int A_BYTES = BM * BK * 2;
     static constexpr int B_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int XCH_BYTES = NG * BM * 8;                      // LN partial sums, one float2 per row and group
+    static constexpr int XCH_BYTES = NG * BM * 8 + 2 * BM * 8;         // LN partial sums per row and group + 2 peer slots (cluster LN)
     static constexpr int SMEM = STAGES * STAGE_BYTES + NG * GROUP_SCRATCH + XCH_BYTES + 256 /*barriers + tmem slot*/;
-    static_assert((2 * STAGES + 4) * 8 + 4 <= 256, "barrier region");
+    static_assert((2 * STAGES + 6) * 8 + 4 <= 256, "barrier region");
     static_assert(SMEM <= 227 * 1024, "shared memory budget");
 };
 
@@ -73,6 +73,7 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 struct TcParams {
     const float* bias; const __nv_bfloat16* res; const float* res32; float* out32; const float* gamma; const float* beta;
     int T, K, N, taps, act, tiles_per_utt, m_tiles, n_chunks, n_out, out_f32;
+    int cluster;                 // TC_LN with N = 512: 2 CTAs own one 256-column half each and swap row sums over DSMEM
     float eps;
     // fused depthwise epilogue (TC_GLU_DW / TC_RES_ACT_DW): a tile's 128 rows are frames
     // [t0 - halo, t0 + 128 - halo); rows_out = 128 - 2*halo frames are produced per tile
@@ -160,18 +161,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     extern __shared__ __align__(1024) unsigned char smem[];                  // SWIZZLE_128B tiles need 1024-B alignment
     unsigned char* scratch = smem + STAGES * C::STAGE_BYTES;                 // NG x GROUP_SCRATCH
     float2* s_xch = reinterpret_cast<float2*>(scratch + NG * GROUP_SCRATCH); // [NG][BM] LN partial (sum, sumsq)
+    float2* s_peer = s_xch + NG * BM;                                        // [2][BM] row sums written by the peer CTA
     uint64_t* bars = reinterpret_cast<uint64_t*>(scratch + NG * GROUP_SCRATCH + C::XCH_BYTES);
-    // bars: full[STAGES], empty[STAGES], tfull[2], tempty[2]
+    // bars: full[STAGES], empty[STAGES], tfull[2], tempty[2], xbar[2] (peer row sums have landed)
     const uint32_t bar0 = smem_u32(bars);
     auto full_bar = [&](int s) { return bar0 + 8u * s; };
     auto empty_bar = [&](int s) { return bar0 + 8u * (STAGES + s); };
     auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * STAGES + a); };
     auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * STAGES + 2 + a); };
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+    auto xbar = [&](int a) { return bar0 + 8u * (2 * STAGES + 4 + a); };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 6);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr bool is_ln = EPI == TC_LN;
-    const int nbu = is_ln ? p.n_chunks : 1;                                  // accumulator chunks per unit
+    const int cl = is_ln ? p.cluster : 1;                                    // CTAs per cluster (cluster LayerNorm)
+    const uint32_t crank = cl > 1 ? cluster_ctarank() : 0;
+    const int u_first = blockIdx.x / cl, u_step = gridDim.x / cl;
+    const int nbu = is_ln ? (cl > 1 ? 1 : p.n_chunks) : 1;                   // accumulator chunks per unit (this CTA)
     const int units = is_ln ? p.m_tiles : p.m_tiles * p.n_chunks;
     const int acc_stages = (512 / (nbu * BN)) >= 2 ? 2 : 1;
     const int kb_per_tap = p.K / BK;
@@ -185,7 +191,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), NG * 128); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), NG * 128); mbar_init(xbar(a), BM); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {                                                         // TMEM: all 512 columns
@@ -193,7 +199,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
-    __syncthreads();
+    if (cl > 1) cluster_sync_all(); else __syncthreads();                    // peers' barriers are initialised before anyone arrives
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -201,9 +207,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         // ================================ TMA producer ================================
         if (lane == 0) {
             int s = 0; uint32_t ph = 0;
-            for (int u = blockIdx.x; u < units; u += gridDim.x) {
+            for (int u = u_first; u < units; u += u_step) {
                 const int m = is_ln ? u : u / p.n_chunks;
-                const int nb0 = is_ln ? 0 : u % p.n_chunks;
+                const int nb0 = is_ln ? (int)crank : u % p.n_chunks;
                 const int b = m / p.tiles_per_utt, t0 = (m % p.tiles_per_utt) * p.rows_out - p.halo;
                 for (int j = 0; j < nbu; ++j) {
                     const int n0 = (nb0 + j) * BN;
@@ -224,7 +230,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         if (lane == 0) {
             constexpr uint32_t idesc = make_idesc(BN);
             int s = 0; uint32_t ph = 0; int it = 0;
-            for (int u = blockIdx.x; u < units; u += gridDim.x, ++it) {
+            for (int u = u_first; u < units; u += u_step, ++it) {
                 const int a = it % acc_stages;
                 const uint32_t aph = (uint32_t)(it / acc_stages) & 1u;
                 mbar_wait(tempty_bar(a), aph ^ 1);
@@ -259,9 +265,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const uint32_t stg_u32 = smem_u32(stg);
         const int bar_id = 1 + group;
         int it = 0;
-        for (int u = blockIdx.x; u < units; u += gridDim.x, ++it) {
+        for (int u = u_first; u < units; u += u_step, ++it) {
             const int m = is_ln ? u : u / p.n_chunks;
-            const int nb0 = is_ln ? 0 : u % p.n_chunks;
+            const int nb0 = is_ln ? (int)crank : u % p.n_chunks;
             const int b = m / p.tiles_per_utt, t0 = (m % p.tiles_per_utt) * p.rows_out - p.halo;   // frame of tile row 0
             const int a = it % acc_stages;
             const uint32_t aph = (uint32_t)(it / acc_stages) & 1u;
@@ -272,16 +278,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const uint32_t acc = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(a * nbu * BN);
 
             if (EPI == TC_LN) {
-                // ---- bias (+ residual) + LayerNorm over the whole row (row = nbu chunks side by side) ----
-                const int ncols = p.N / NG, c_begin = group * ncols;          // this thread's slice of the row
+                // ---- bias (+ residual) + LayerNorm over the whole row.  The row is nbu chunks side by side
+                // in this CTA's TMEM; with cl = 2 the other half lives in the peer CTA and the two swap
+                // their (sum, sum of squares) over distributed shared memory ----
+                const int ncols = nbu * BN / NG, c_begin = group * ncols;     // this thread's slice of the accumulator
+                const int gbase = nb0 * BN;                                   // global column of accumulator column 0
                 float s1 = 0.f, s2 = 0.f;
                 for (int c = c_begin; c < c_begin + ncols; c += 32) {
                     float v[32];
                     tmem_ld32(acc + c, v);
-                    add_vec32(v, p.bias + c);
+                    add_vec32(v, p.bias + gbase + c);
                     if (row_ok) {
-                        if (p.res32) add_f32x32(v, p.res32 + grow * p.N + c);
-                        else if (p.res) add_res32(v, p.res + grow * p.N + c);
+                        if (p.res32) add_f32x32(v, p.res32 + grow * p.N + gbase + c);
+                        else if (p.res) add_res32(v, p.res + grow * p.N + gbase + c);
                     }
 #pragma unroll
                     for (int i = 0; i < 32; ++i) { s1 += v[i]; s2 = fmaf(v[i], v[i], s2); }
@@ -291,34 +300,44 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 float t1 = 0.f, t2 = 0.f;
 #pragma unroll
                 for (int gq = 0; gq < NG; ++gq) { const float2 o = s_xch[gq * BM + r]; t1 += o.x; t2 += o.y; }
+                if (cl > 1) {
+                    const int pb = it & 1;
+                    if (group == 0) {                                         // one thread per row ships the half-row sums
+                        st_cluster_f2(map_to_cta(smem_u32(s_peer + pb * BM + r), crank ^ 1), make_float2(t1, t2));
+                        mbar_arrive_cluster(map_to_cta(xbar(pb), crank ^ 1));
+                    }
+                    mbar_wait_cluster(xbar(pb), (uint32_t)(it >> 1) & 1u);
+                    const float2 o = s_peer[pb * BM + r];
+                    t1 += o.x; t2 += o.y;
+                }
                 epi_bar(NG + 1, NG * 128);                                    // all partners have read before the next tile writes
                 const float mean = t1 / (float)p.N;
                 const float rstd = rsqrtf(fmaxf(t2 / (float)p.N - mean * mean, 0.f) + p.eps);
                 for (int c = c_begin; c < c_begin + ncols; c += 32) {
                     float v[32];
                     tmem_ld32(acc + c, v);
-                    add_vec32(v, p.bias + c);
+                    add_vec32(v, p.bias + gbase + c);
                     if (row_ok) {
-                        if (p.res32) add_f32x32(v, p.res32 + grow * p.N + c);
-                        else if (p.res) add_res32(v, p.res + grow * p.N + c);
+                        if (p.res32) add_f32x32(v, p.res32 + grow * p.N + gbase + c);
+                        else if (p.res) add_res32(v, p.res + grow * p.N + gbase + c);
                     }
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
-                        const float4 gm = __ldg(reinterpret_cast<const float4*>(p.gamma + c) + i);
-                        const float4 bt = __ldg(reinterpret_cast<const float4*>(p.beta + c) + i);
+                        const float4 gm = __ldg(reinterpret_cast<const float4*>(p.gamma + gbase + c) + i);
+                        const float4 bt = __ldg(reinterpret_cast<const float4*>(p.beta + gbase + c) + i);
                         v[4 * i + 0] = fmaf((v[4 * i + 0] - mean) * rstd, gm.x, bt.x);
                         v[4 * i + 1] = fmaf((v[4 * i + 1] - mean) * rstd, gm.y, bt.y);
                         v[4 * i + 2] = fmaf((v[4 * i + 2] - mean) * rstd, gm.z, bt.z);
                         v[4 * i + 3] = fmaf((v[4 * i + 3] - mean) * rstd, gm.w, bt.w);
                     }
-                    if (p.out32 && row_ok) store_f32x32(p.out32 + grow * p.N + c, v);   // fp32 copy: the next residual stream
+                    if (p.out32 && row_ok) store_f32x32(p.out32 + grow * p.N + gbase + c, v);   // fp32 copy: the next residual stream
                     const int cb = (c - c_begin) & 32;                        // which half of the 64-column staging tile
                     if (cb == 0) { if (leader) tma_wait_read0(); epi_bar(bar_id, 128); }
                     stage_store32(stg, r, cb, v);
                     if (cb == 32) {
                         fence_async_smem();
                         epi_bar(bar_id, 128);
-                        if (leader) { tma_store_3d(&map_out, stg_u32, c - 32, t0, b); tma_commit(); }
+                        if (leader) { tma_store_3d(&map_out, stg_u32, gbase + c - 32, t0, b); tma_commit(); }
                     }
                 }
             } else if (EPI == TC_GLU_DW || EPI == TC_RES_ACT_DW) {
@@ -421,7 +440,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
 
     tc_fence_before();
-    __syncthreads();
+    if (cl > 1) cluster_sync_all(); else __syncthreads();                    // no CTA exits while its peer may still write to it
     if (warp == 2) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
@@ -491,9 +510,17 @@ static int launch_one(const CUtensorMap& ma, const CUtensorMap& mw, const CUtens
                       cudaStream_t st) {
     auto kern = gemm_tc_kernel<BN, EPI>;
     ASRB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::SMEM));
-    int grid = sm_count();
-    if (grid > units) grid = units;
-    kern<<<grid, TcCfg<BN>::THREADS, TcCfg<BN>::SMEM, st>>>(ma, mw, mo, p);
+    const int cl = p.cluster;
+    int grid = sm_count() / cl * cl;
+    if (grid > units * cl) grid = units * cl;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(TcCfg<BN>::THREADS);
+    cfg.dynamicSmemBytes = TcCfg<BN>::SMEM; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    ASRB_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mw, mo, p));
     ASRB_LAUNCH_CHECK();
     return ASRB_OK;
 }
@@ -525,6 +552,7 @@ int launch_gemm_tc(const TcGemmArgs& a, cudaStream_t st) {
     p.tiles_per_utt = (int)((a.T + rows_out - 1) / rows_out);
     p.m_tiles = (int)(a.B * p.tiles_per_utt);
     p.n_chunks = a.N / bn; p.n_out = n_out; p.eps = a.eps; p.out_f32 = a.out_f32;
+    p.cluster = (a.epilogue == TC_LN && bn == 256 && a.N == 512) ? 2 : 1;     // the 128 x 512 row block fills TMEM: split it over a CTA pair
     const int units = a.epilogue == TC_LN ? p.m_tiles : p.m_tiles * p.n_chunks;
     static const char* const tags[6] = {"gemm_tc_bias_act", "gemm_tc_glu", "gemm_tc_res_act", "gemm_tc_layernorm",
                                         "gemm_tc_glu_dw15_silu", "gemm_tc_res_gelu_dw3_gelu"};
