@@ -68,8 +68,20 @@ class ShardedEncoder:
     """
 
     def __init__(self, compute: Callable[..., torch.Tensor], group=None, micro: int = 0, gather: bool = True,
-                 shape_of: Optional[Callable[[torch.Tensor], Tuple[int, int, torch.dtype]]] = None):
+                 shape_of: Optional[Callable[[torch.Tensor], Tuple[int, int, torch.dtype]]] = None,
+                 overlap_steps: bool = False):
+        """``overlap_steps``: do not wait for a call's exchange before returning; it is waited for at the
+        end of the NEXT call (or by ``finish()``), so the gather of step i rides under the compute of
+        step i+1.  The local block of the returned tensor is always valid on the current stream; the
+        peers' blocks are valid after the next call / ``finish()``."""
         self.compute, self.group, self.micro, self.gather, self.shape_of = compute, group, micro, gather, shape_of
+        self.overlap_steps = overlap_steps
+        self._inflight = []
+
+    def finish(self):
+        for w in self._inflight:
+            w.wait()
+        self._inflight = []
 
     def _run(self, waves, out=None):
         if out is not None and self.shape_of is not None:
@@ -118,6 +130,11 @@ class ShardedEncoder:
                 ops.append(dist.P2POp(dist.isend, out[lo + s: lo + e], peer, self.group))
                 ops.append(dist.P2POp(dist.irecv, out[r * n_local + s: r * n_local + e], peer, self.group))
             pending.extend(dist.batch_isend_irecv(ops))
-        for w in pending:
-            w.wait()
+        if self.overlap_steps:
+            prev, self._inflight = self._inflight, pending
+            for w in prev:
+                w.wait()
+        else:
+            for w in pending:
+                w.wait()
         return out

@@ -12,8 +12,8 @@ per-utterance pooled hidden state inside the timed region).  `roofline`: the dom
 (tcgen05 conv-GEMM + LayerNorm) from per-launch CUDA events.  `cpu_baseline`: the oracle
 (port of the reference) on this box's host cores on a bounded sample.
 Under torchrun (N > 1) each rank runs its own 64-clip shard (weak scaling) and the encoder
-outputs are all-gathered over NCCL, pipelined per micro-batch; the gather is inside the
-timed region.
+outputs are exchanged over NCCL (grouped send/recv straight into the gathered tensor); the
+exchange of step i overlaps the compute of step i+1 and all of it is inside the timed region.
 """
 import argparse
 import json
@@ -142,7 +142,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--enc", type=int, default=0, help="1 = with the optional TransformerEncoderLayer (model.py:138)")
-    ap.add_argument("--micro", type=int, default=16, help="micro-batch for the pipelined gather (N > 1)")
+    ap.add_argument("--micro", type=int, default=0, help="micro-batch inside a step for the gather (N > 1); 0 = whole shard")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -180,13 +180,16 @@ def main():
     def hot(w, out=None):
         return enc.forward_pcm(w, fe, out=out)
 
+    # N > 1: the exchange of step i overlaps the compute of step i+1 (waited for one step later)
     sharded = ShardedEncoder(hot, micro=args.micro if world > 1 else 0, gather=world > 1,
-                             shape_of=lambda w: (fe.num_frames(w.shape[1]), DIMS, torch.bfloat16))
+                             shape_of=lambda w: (fe.num_frames(w.shape[1]), DIMS, torch.bfloat16),
+                             overlap_steps=world > 1)
 
     def step_resident():
         return sharded(pcm, total=B * world)
 
     def sync():
+        sharded.finish()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()

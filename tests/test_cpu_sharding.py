@@ -35,7 +35,14 @@ def _worker(rank, world, port, total, micro, q):
         out = ShardedEncoder(_fake_compute, micro=micro)(waves[lo:hi], total=total)
         ok = torch.equal(out, _fake_compute(waves))
         out2, _ = gather_outputs(_fake_compute(waves[lo:hi]), total)
-        q.put((rank, bool(ok), bool(torch.equal(out2, _fake_compute(waves)))))
+        ok2 = torch.equal(out2, _fake_compute(waves))
+        if total % world == 0:                       # deferred wait: step i's exchange finishes during step i+1
+            se = ShardedEncoder(_fake_compute, micro=micro, overlap_steps=True)
+            o1 = se(waves[lo:hi], total=total)
+            o2 = se(waves[lo:hi] * 2, total=total)
+            se.finish()
+            ok2 = ok2 and torch.equal(o1, _fake_compute(waves)) and torch.equal(o2, _fake_compute(waves * 2))
+        q.put((rank, bool(ok), bool(ok2)))
     finally:
         dist.destroy_process_group()
 
