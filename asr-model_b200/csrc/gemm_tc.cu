@@ -379,15 +379,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     const int gcol = gc + lane;
                     const float dwb = __ldg(p.dw_b + gcol);
                     const float* xcol = xbuf + slice * 32 * XPITCH + lane;
-                    if (p.kw == 15) dw_columns<15>(xcol, slice * 32, p.dw_w, p.n_out, gcol, dwb, p.act2, o);
-                    else dw_columns<3>(xcol, slice * 32, p.dw_w, p.n_out, gcol, dwb, p.act2, o);
                     const int tout0 = t0 + p.halo + slice * 32;               // frame of this thread's first output row
                     const int nrow = min(min(32, p.rows_out - slice * 32), p.T - tout0);   // valid outputs of this thread
-                    if (p.pos) {
+                    if (p.pos) {                                              // last block: + sinusoids; loads issued before the taps
+                        float pv[32];
 #pragma unroll
-                        for (int i = 0; i < 32; ++i)
-                            if (i < nrow) o[i] += __ldg(p.pos + (int64_t)(tout0 + i) * p.n_out + gcol);
-                    }
+                        for (int i = 0; i < 32; ++i) pv[i] = (i < nrow) ? __ldg(p.pos + (int64_t)(tout0 + i) * p.n_out + gcol) : 0.f;
+                        dw_columns<3>(xcol, slice * 32, p.dw_w, p.n_out, gcol, dwb, p.act2, o);
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) o[i] += pv[i];
+                    } else if (p.kw == 15) dw_columns<15>(xcol, slice * 32, p.dw_w, p.n_out, gcol, dwb, p.act2, o);
+                    else dw_columns<3>(xcol, slice * 32, p.dw_w, p.n_out, gcol, dwb, p.act2, o);
                     if (p.out32) {
 #pragma unroll
                         for (int i = 0; i < 32; ++i)
@@ -533,7 +535,7 @@ int launch_gemm_tc(const TcGemmArgs& a, cudaStream_t st) {
     const bool glu = a.epilogue == TC_GLU || a.epilogue == TC_GLU_DW;
     const bool dw = a.epilogue == TC_GLU_DW || a.epilogue == TC_RES_ACT_DW;
     const int n_out = glu ? a.N / 2 : a.N;
-    if (dw && ((a.dw_kw != 3 && a.dw_kw != 15) || !a.dw_w || !a.dw_b || a.out_f32 || a.taps != 1))
+    if (dw && ((a.dw_kw != 3 && a.dw_kw != 15) || !a.dw_w || !a.dw_b || a.out_f32 || a.taps != 1 || (a.pos && a.dw_kw != 3)))
         return fail(ASRB_E_ARG, "tcgen05 GEMM: bad fused-depthwise arguments");
     if (a.epilogue == TC_RES_ACT_DW && !a.res) return fail(ASRB_E_ARG, "tcgen05 GEMM: residual required");
     const int halo = dw ? a.dw_kw / 2 : 0, rows_out = BM - 2 * halo;

@@ -59,9 +59,12 @@ class LogMel:
         self._ws: Optional[torch.Tensor] = None
 
     def __del__(self):
-        if getattr(self, "_plan", None) and self._plan.value:
-            self.lib.asrb_logmel_plan_destroy(self._plan)
-            self._plan = C.c_void_p()
+        try:
+            if getattr(self, "_plan", None) is not None and self._plan.value:
+                self.lib.asrb_logmel_plan_destroy(self._plan)
+                self._plan = None
+        except Exception:            # interpreter shutdown
+            pass
 
     @property
     def handle(self) -> C.c_void_p:

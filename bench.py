@@ -48,7 +48,7 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """Samples SM clock and throttle reasons of one GPU every 100 ms while the timed region runs."""
+    """Samples SM clock and throttle reasons of one GPU every 5 ms while the timed region runs."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
@@ -79,7 +79,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(nm)
             except Exception:
                 pass
-            self._stop_evt.wait(0.1)
+            self._stop_evt.wait(0.005)
 
     def stop(self):
         self._stop_evt.set()
@@ -243,7 +243,7 @@ def main():
             main_stream.wait_event(ready[k])
             h = sharded(dev_in[k], total=B * world)
             lo = rank * B
-            pooled_host[k].copy_(h[lo:lo + B].float().mean(dim=1), non_blocking=True)
+            pooled_host[k].copy_(torch.mean(h[lo:lo + B], dim=1, dtype=torch.float32), non_blocking=True)
             freed[k].record(main_stream)
 
     run_e2e(3)
@@ -276,19 +276,24 @@ def main():
                    "share": d["ms"] / psteps / step_ms_prof if step_ms_prof else None,
                    "tflops": d["flops"] / d["ms"] / 1e9 if d["ms"] and d["flops"] else None,
                    "gbs": d["bytes"] / d["ms"] / 1e6 if d["ms"] else None} for t, d in by.items()}
+    traffic = {}
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["bytes_per_launch"]
+    except Exception:
+        pass
     dom = max(by, key=lambda t: by[t]["ms"])
     dd = by[dom]
     tensor_bound = dom.startswith("gemm_tc")
     if tensor_bound:
         achieved = dd["flops"] / dd["ms"] / 1e9            # TFLOP/s
         roof = {"kernel": dom, "bound": "tensor", "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
-                "frac": achieved / pk["tf_sustained"], "traffic": None,
+                "frac": achieved / pk["tf_sustained"], "traffic": traffic.get(dom), "traffic_unit": "bytes per launch (ncu, profiles/traffic.json)",
                 "peak_source": pk["src"] + " (sustained bf16, kernel timed inside a long step)",
                 "avg_launch_ms": dd["ms"] / dd["n"], "flops_per_launch": dd["flops"] / dd["n"]}
     else:
         achieved = dd["bytes"] / dd["ms"] / 1e6            # GB/s
         roof = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                "frac": achieved / pk["hbm_gbs"], "traffic": None, "peak_source": pk["src"],
+                "frac": achieved / pk["hbm_gbs"], "traffic": traffic.get(dom), "peak_source": pk["src"],
                 "avg_launch_ms": dd["ms"] / dd["n"], "bytes_per_launch": dd["bytes"] / dd["n"]}
     enc_flops = flops_per_frame(bool(args.enc), T) * B * T
     whole = {"encoder_algorithmic_tflop_per_step": enc_flops / 1e12,
