@@ -18,7 +18,7 @@ import importlib as _importlib
 __version__ = "0.1.0"
 
 _LAZY = {
-    "log_mel": "frontend", "extract_features": "frontend", "LogMel": "frontend",
+    "log_mel": "frontend", "extract_features": "frontend", "LogMel": "frontend", "waveform_feature": "frontend",
     "AudioEncoder": "encoder", "AudioAttention": "attention",
     "ShardedEncoder": "sharded", "gather_outputs": "sharded", "shard_range": "sharded",
     "lib": "_lib", "synth": "synth",

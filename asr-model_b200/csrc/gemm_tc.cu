@@ -127,11 +127,14 @@ __device__ __forceinline__ void xbuf_store_row(float* xrow, const float (&v)[32]
     for (int i = 0; i < 32; ++i) xrow[i] = v[i];
 }
 
-// Phase 2: this thread owns column `c` and output rows [o0, o0 + 32) of the tile; the input row of
-// output o and tap j is o + j.  Results stay in registers (the buffer is about to be reused).
+// Phase 2: this thread owns one column and output rows [o0, o0 + OPT) of the tile (OPT = a quarter of
+// the tile's BM - KW + 1 output rows); the input row of output o and tap j is o + j.  Results stay in
+// registers (the buffer is about to be reused).
+template <int KW> struct DwSlice { static constexpr int OPT = (BM - KW + 1 + 3) / 4; };
 template <int KW>
 __device__ __forceinline__ void dw_columns(const float* xcol /* &xbuf[o0][c] */, int o0, const float* __restrict__ w,
                                            int D, int gcol, float bias, int act2, float (&out)[32]) {
+    constexpr int OPT = DwSlice<KW>::OPT;
     float wv[KW];
 #pragma unroll
     for (int j = 0; j < KW; ++j) wv[j] = __ldg(w + (int64_t)j * D + gcol);
@@ -141,13 +144,17 @@ __device__ __forceinline__ void dw_columns(const float* xcol /* &xbuf[o0][c] */,
     for (int j = 0; j < KW - 1; ++j) win[j + 1] = (j < lim) ? xcol[j * XPITCH] : 0.f;
 #pragma unroll
     for (int o = 0; o < 32; ++o) {
+        if (o < OPT) {
 #pragma unroll
-        for (int j = 0; j < KW - 1; ++j) win[j] = win[j + 1];
-        win[KW - 1] = (o + KW - 1 < lim) ? xcol[(o + KW - 1) * XPITCH] : 0.f;
-        float a = bias;
+            for (int j = 0; j < KW - 1; ++j) win[j] = win[j + 1];
+            win[KW - 1] = (o + KW - 1 < lim) ? xcol[(o + KW - 1) * XPITCH] : 0.f;
+            float a = bias;
 #pragma unroll
-        for (int j = 0; j < KW; ++j) a = fmaf(wv[j], win[j], a);
-        out[o] = a;
+            for (int j = 0; j < KW; ++j) a = fmaf(wv[j], win[j], a);
+            out[o] = a;
+        } else {
+            out[o] = 0.f;
+        }
     }
     act_fast32(out, act2);
 }
@@ -378,28 +385,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     float o[32];
                     const int gcol = gc + lane;
                     const float dwb = __ldg(p.dw_b + gcol);
-                    const float* xcol = xbuf + slice * 32 * XPITCH + lane;
-                    const int tout0 = t0 + p.halo + slice * 32;               // frame of this thread's first output row
-                    const int nrow = min(min(32, p.rows_out - slice * 32), p.T - tout0);   // valid outputs of this thread
+                    const int opt = p.kw == 15 ? DwSlice<15>::OPT : DwSlice<3>::OPT;   // outputs per thread
+                    const int o0 = slice * opt;
+                    const float* xcol = xbuf + o0 * XPITCH + lane;
+                    const int tout0 = t0 + p.halo + o0;                       // frame of this thread's first output row
+                    const int nrow = min(min(opt, p.rows_out - o0), p.T - tout0);   // valid outputs of this thread
                     if (p.pos) {                                              // last block: + sinusoids; loads issued before the taps
                         float pv[32];
 #pragma unroll
                         for (int i = 0; i < 32; ++i) pv[i] = (i < nrow) ? __ldg(p.pos + (int64_t)(tout0 + i) * p.n_out + gcol) : 0.f;
-                        dw_columns<3>(xcol, slice * 32, p.dw_w, p.n_out, gcol, dwb, p.act2, o);
+                        dw_columns<3>(xcol, o0, p.dw_w, p.n_out, gcol, dwb, p.act2, o);
 #pragma unroll
                         for (int i = 0; i < 32; ++i) o[i] += pv[i];
-                    } else if (p.kw == 15) dw_columns<15>(xcol, slice * 32, p.dw_w, p.n_out, gcol, dwb, p.act2, o);
-                    else dw_columns<3>(xcol, slice * 32, p.dw_w, p.n_out, gcol, dwb, p.act2, o);
+                    } else if (p.kw == 15) dw_columns<15>(xcol, o0, p.dw_w, p.n_out, gcol, dwb, p.act2, o);
+                    else dw_columns<3>(xcol, o0, p.dw_w, p.n_out, gcol, dwb, p.act2, o);
                     if (p.out32) {
 #pragma unroll
                         for (int i = 0; i < 32; ++i)
                             if (i < nrow) p.out32[((int64_t)b * p.T + tout0 + i) * p.n_out + gcol] = o[i];
                     }
                     epi_bar(bar_id, 128);                                     // everyone is done reading xbuf
-                    __nv_bfloat16* tile = reinterpret_cast<__nv_bfloat16*>(stg) + slice * 32 * 32 + lane;   // [rows_out][32] bf16
+                    __nv_bfloat16* tile = reinterpret_cast<__nv_bfloat16*>(stg) + o0 * 32 + lane;   // [rows_out][32] bf16
 #pragma unroll
                     for (int i = 0; i < 32; ++i)
-                        if (slice * 32 + i < p.rows_out) tile[i * 32] = __float2bfloat16_rn(o[i]);
+                        if (i < opt && o0 + i < p.rows_out) tile[i * 32] = __float2bfloat16_rn(o[i]);
                     fence_async_smem();
                     epi_bar(bar_id, 128);
                     if (leader) { tma_store_3d(&map_out, stg_u32, gc, t0 + p.halo, b); tma_commit(); }

@@ -370,3 +370,45 @@ extern "C" int asrb_logmel_f32(const asrb_logmel_plan* pl, const float* pcm, int
     ASRB_LAUNCH_CHECK();
     return ASRB_OK;
 }
+
+// ------------------------------------------------------------------------------------------
+// "waveform" feature: the reference resamples the PCM to the frame rate
+// with F.adaptive_avg_pool1d(audio, target) (essentials.py:493-503); output i is the mean of
+// x[floor(i N / target) : ceil((i + 1) N / target)).  One warp per output, coalesced reads.
+// ------------------------------------------------------------------------------------------
+namespace asrb {
+__global__ void waveform_pool_kernel(const float* __restrict__ pcm, int64_t stride, int64_t n, int64_t target,
+                                     float* __restrict__ out, int64_t total) {
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (w >= total) return;
+    const int lane = threadIdx.x & 31;
+    const int64_t b = w / target, i = w - b * target;
+    const int64_t s = (i * n) / target;
+    const int64_t e = ((i + 1) * n + target - 1) / target;
+    const float* x = pcm + b * stride;
+    float acc = 0.f;
+    for (int64_t k = s + lane; k < e; k += 32) acc += x[k];
+    acc = warp_sum(acc);
+    if (lane == 0) out[w] = acc / (float)(e - s);
+}
+}  // namespace asrb
+
+extern "C" int asrb_waveform_pool_f32(const float* pcm, int64_t batch, int64_t n_samples, int64_t pcm_stride,
+                                      int64_t target, float* out, void* stream) {
+    if (batch < 0 || n_samples < 0 || pcm_stride < n_samples || target < 0)
+        return fail(ASRB_E_ARG, "asrb_waveform_pool_f32: bad shape");
+    if (batch == 0 || target == 0) return ASRB_OK;
+    if (!pcm || !out) return fail(ASRB_E_ARG, "asrb_waveform_pool_f32: NULL tensor");
+    if (target >= n_samples)
+        return fail(ASRB_E_ARG, "asrb_waveform_pool_f32: target %lld >= %lld samples (the reference interpolates there; unsupported)",
+                    (long long)target, (long long)n_samples);
+    ASRB_TRY(require_sm100());
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t total = batch * target;
+    ProfScope ps("waveform_pool", st, 0.0, 4.0 * batch * ((double)n_samples + target));
+    const int64_t blocks = (total * 32 + 255) / 256;
+    if (blocks > 0x7fffffff) return fail(ASRB_E_ARG, "asrb_waveform_pool_f32: too large");
+    waveform_pool_kernel<<<(unsigned)blocks, 256, 0, st>>>(pcm, pcm_stride, n_samples, target, out, total);
+    ASRB_LAUNCH_CHECK();
+    return ASRB_OK;
+}

@@ -123,14 +123,37 @@ def log_mel(wave: torch.Tensor, n_mels: int = 128, n_fft: int = 1024, hop_length
     return _plan_for(n_mels, n_fft, hop_length, sample_rate, wave.device)(wave, lengths)
 
 
+def waveform_feature(wave: torch.Tensor, hop_length: int = HOP, sample_rate: int = SAMPLE_RATE) -> torch.Tensor:
+    """The reference's ``waveform`` feature (essentials.py:493-503), batched: ``[B, N]`` (or ``[N]``) ->
+    ``[B, 1, target]`` with ``target = int((N / sample_rate) * (sample_rate // hop_length))`` evaluated in
+    Python floats exactly like the reference (so e.g. N = 4640 gives 28, not 29)."""
+    if not wave.is_cuda:
+        raise _lib.AsrbError("waveform_feature needs a CUDA tensor: there is no CPU path")
+    lib = _lib.load()
+    squeeze = wave.dim() == 1
+    if squeeze:
+        wave = wave.unsqueeze(0)
+    wave = wave.float()
+    if wave.stride(-1) != 1:
+        wave = wave.contiguous()
+    B, N = wave.shape
+    assert sample_rate % hop_length == 0                     # exact_div, essentials.py:296-298
+    target = int((N / sample_rate) * (sample_rate // hop_length))
+    out = torch.empty(B, 1, target, device=wave.device, dtype=torch.float32)
+    with torch.cuda.device(wave.device):
+        _lib.check(lib.asrb_waveform_pool_f32(wave.data_ptr(), B, N, wave.stride(0) if B > 1 else max(N, 1), target,
+                                              out.data_ptr(), _lib.stream_ptr()), "asrb_waveform_pool_f32")
+    return out[0] if squeeze else out
+
+
 def extract_features(batch, tokenizer=None, spectrogram=False, pitch=False, waveform=False,
                      harmonics=False, aperiodics=False, phase=False, hilbert=False, pitch_tokens=False,
                      hop_length=160, sample_rate=16000, mels=128, n_fft=1024, device="cuda"):
-    """Per-utterance drop-in for the reference ``extract_features`` (essentials.py:423-521),
-    spectrogram branch only -- the other branches are CPU WORLD-vocoder features outside
-    this path and raise."""
-    if pitch or waveform or harmonics or aperiodics or phase or hilbert or pitch_tokens:
-        raise NotImplementedError("only spectrogram=True is on the accelerated path")
+    """Per-utterance drop-in for the reference ``extract_features`` (essentials.py:423-521):
+    the spectrogram branch and the waveform (average-pooled PCM) branch.  The other branches
+    are CPU WORLD-vocoder features outside this path and raise."""
+    if pitch or harmonics or aperiodics or phase or hilbert or pitch_tokens:
+        raise NotImplementedError("only spectrogram=True / waveform=True are on the accelerated path")
     labels = tokenizer.encode(batch["transcription" if "transcription" in batch else "sentence"]) \
         if tokenizer is not None else None
     audio = batch["audio"]
@@ -140,6 +163,8 @@ def extract_features(batch, tokenizer=None, spectrogram=False, pitch=False, wave
         wave = audio.float()
     else:
         raise TypeError("Invalid wave_data format.")            # essentials.py:318
-    s_tensor = log_mel(wave.to(device), mels, n_fft, hop_length, sample_rate) if spectrogram else None
-    return {"waveform": None, "spectrogram": s_tensor, "pitch_tokens": None, "pitch": None,
+    wave = wave.to(device)
+    s_tensor = log_mel(wave, mels, n_fft, hop_length, sample_rate) if spectrogram else None
+    w_tensor = waveform_feature(wave, hop_length, sample_rate) if waveform else None       # [1, target]
+    return {"waveform": w_tensor, "spectrogram": s_tensor, "pitch_tokens": None, "pitch": None,
             "harmonic": None, "aperiodic": None, "labels": labels, "phase": None}

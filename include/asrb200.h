@@ -81,6 +81,14 @@ int asrb_logmel_f32(const asrb_logmel_plan* plan,
                     float* out,
                     void* workspace, size_t workspace_bytes, void* stream);
 
+/* The `waveform` feature of extract_features (essentials.py:493-503): PCM resampled to the frame
+ * rate with adaptive average pooling, out[b][i] = mean(pcm[b][floor(i n/target) : ceil((i+1) n/target))).
+ * `target` is computed by the binding exactly as the reference does
+ * (int((n / sample_rate) * (sample_rate // hop))).  pcm [batch][pcm_stride], out [batch][target] fp32 device.
+ * target < n_samples (the reference's linear-interpolation branch for shorter inputs is not built). */
+int asrb_waveform_pool_f32(const float* pcm, int64_t batch, int64_t n_samples, int64_t pcm_stride,
+                           int64_t target, float* out, void* stream);
+
 /* ------------------------------------------------------------------------------------
  * Encoder.  Replaces AudioEncoder.__init__/forward (model.py:120-169) with norm=False:
  * conv stem, `layer` x [GELU, weight-normed Conv1d k3, channel LayerNorm, ConvLite, GELU,

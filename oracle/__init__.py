@@ -27,6 +27,7 @@ from .logmel import (  # noqa: F401
     log_mel_utterance,
     log_mel_batch,
     collate_spectrograms,
+    waveform_feature,
 )
 from .encoder import (  # noqa: F401
     sinusoids,

@@ -124,3 +124,17 @@ def collate_spectrograms(items: List[torch.Tensor], t_max: Optional[int] = None)
     out = [torch.nn.functional.pad(i, (0, t_max - i.shape[-1]), mode="constant", value=0)
            for i in items]
     return torch.stack(out)
+
+
+def waveform_feature(wave: torch.Tensor, sample_rate: int = SAMPLE_RATE, hop: int = HOP) -> torch.Tensor:
+    """The ``waveform`` branch of ``extract_features`` (essentials.py:493-510) for one utterance ``[N]``:
+    ``target = int((N / sr) * (sr // hop))`` (Python float arithmetic, as written in the reference),
+    ``adaptive_avg_pool1d`` when the clip is longer than the target -> ``[1, target]``."""
+    n = wave.shape[-1]
+    target = int((n / sample_rate) * (sample_rate // hop))
+    aud = wave.float().unsqueeze(0).unsqueeze(0)
+    if n > target:
+        w = torch.nn.functional.adaptive_avg_pool1d(aud, target)
+    else:
+        w = torch.nn.functional.interpolate(aud, size=target, mode="linear", align_corners=False)
+    return w.squeeze(0)

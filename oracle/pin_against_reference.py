@@ -100,6 +100,15 @@ def main():
         fb = oracle.melscale_fbanks_htk(n_fft // 2 + 1, n_mels)
         assert torch.equal(fb_ref, fb)
         fe[f"fbank_f{n_fft}_m{n_mels}"] = fb.numpy()
+    # waveform feature (essentials.py:493-510) through the reference's own extract_features
+    for kind, n in (("W", 8000), ("H", 4640), ("2", 16037)):
+        wave = synth.make_wave(kind, n)
+        out = essentials.extract_features({"audio": {"array": wave.numpy(), "sampling_rate": 16000}, "transcription": "x"},
+                                          _Tok(), waveform=True, hop_length=160, sample_rate=16000)["waveform"].cpu()
+        ours = oracle.waveform_feature(wave)
+        assert out.shape == ours.shape and torch.equal(out, ours), (kind, n, out.shape, ours.shape)
+        fe[f"waveform_{kind}_{n}"] = out.numpy()
+        report["cases"][f"waveform_{kind}_{n}"] = {"oracle_vs_ref_maxabs": 0.0, "shape": list(out.shape)}
     np.savez_compressed(os.path.join(GOLD, "frontend.npz"), **fe)
 
     # ---------------- sinusoids ----------------

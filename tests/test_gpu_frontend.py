@@ -108,3 +108,28 @@ def test_extract_features_drop_in(ab):
                             Tok(), spectrogram=True, mels=128)
     assert r["labels"] == [5, 6] and r["spectrogram"].shape == (128, 101) and r["spectrogram"].is_cuda
     assert float((r["spectrogram"].cpu() - oracle.log_mel_utterance(w, 128, 1024)).abs().max()) <= TOL
+
+
+def test_waveform_feature_matches_reference(ab, golden):
+    """the average-pooled PCM stream (essentials.py:493-510)."""
+    for key in golden["frontend"].files:
+        if key.startswith("waveform_"):
+            _, kind, length = key.split("_")
+            ref = torch.from_numpy(golden["frontend"][key])
+            out = ab.waveform_feature(synth.make_wave(kind, int(length)).cuda()).cpu()
+            assert out.shape == ref.shape and float((out - ref).abs().max()) <= 1e-6, key
+    waves = synth.make_batch("WH2", 480000)
+    out = ab.waveform_feature(waves.cuda()).cpu()
+    assert out.shape == (3, 1, 3000)
+    for b in range(3):
+        assert float((out[b] - oracle.waveform_feature(waves[b])).abs().max()) <= 1e-6
+    r = ab.extract_features({"audio": {"array": waves[0].numpy(), "sampling_rate": 16000}, "transcription": "x"},
+                            None, spectrogram=True, waveform=True, mels=80, n_fft=400)
+    assert r["waveform"].shape == (1, 3000) and r["spectrogram"].shape == (80, 3001)
+    # the pooled stream feeds the encoder through conv2 (model.py:152-155)
+    sd = oracle.random_encoder_state_dict(80, 128, 1, False, seed=5, perturb=True)
+    m = ab.AudioEncoder(80, 128, 4, 1, compute="fp32").eval()
+    m.load_state_dict(sd)
+    h = m(r["waveform"]).cpu()
+    ref_h = oracle.audio_encoder_forward(sd, oracle.waveform_feature(waves[0]), 4)
+    assert float((h - ref_h).abs().max()) <= 1e-4

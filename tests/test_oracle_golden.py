@@ -106,3 +106,16 @@ def test_encoder_param_count():
     n = sum(int(np.prod(s)) for k, s in spec.items()
             if "running_" not in k and "num_batches" not in k)
     assert n == 6476288
+
+
+def test_waveform_feature_matches_reference_fixtures(golden):
+    n = 0
+    for key in golden["frontend"].files:
+        if key.startswith("waveform_"):
+            _, kind, length = key.split("_")
+            ref = torch.from_numpy(golden["frontend"][key])
+            out = oracle.waveform_feature(synth.make_wave(kind, int(length)))
+            assert out.shape == ref.shape and float((out - ref).abs().max()) <= 1e-7, key
+            n += 1
+    assert n == 3
+    assert oracle.waveform_feature(torch.zeros(4640)).shape == (1, 28)      # the reference's float quirk: 0.29 * 100 -> 28
