@@ -281,19 +281,31 @@ def main():
         traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["bytes_per_launch"]
     except Exception:
         pass
-    dom = max(by, key=lambda t: by[t]["ms"])
-    dd = by[dom]
-    tensor_bound = dom.startswith("gemm_tc")
-    if tensor_bound:
-        achieved = dd["flops"] / dd["ms"] / 1e9            # TFLOP/s
-        roof = {"kernel": dom, "bound": "tensor", "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
-                "frac": achieved / pk["tf_sustained"], "traffic": traffic.get(dom), "traffic_unit": "bytes per launch (ncu, profiles/traffic.json)",
+    # The dominant kernel is the tcgen05 implicit-GEMM `gemm_tc_kernel<BN, EPI>`: one kernel template whose
+    # epilogue variants (stem, k3+LayerNorm, 1x1+GLU+depthwise-15, 1x1+residual+depthwise-3, ...) make up
+    # > 90 % of the step.  The roofline entry aggregates its launches (per launch = totals / launches);
+    # the per-variant numbers are in "kernels".
+    fam = {t: d for t, d in by.items() if t.startswith("gemm_tc")}
+    other = max((t for t in by if t not in fam), key=lambda t: by[t]["ms"], default=None)
+    fam_ms = sum(d["ms"] for d in fam.values())
+    if fam and fam_ms >= (by[other]["ms"] if other else 0.0):
+        n = sum(d["n"] for d in fam.values())
+        fl = sum(d["flops"] for d in fam.values())
+        tr = sum(traffic[t] * (d["n"]) for t, d in fam.items() if t in traffic)
+        tr_n = sum(d["n"] for t, d in fam.items() if t in traffic)
+        achieved = fl / fam_ms / 1e9                       # TFLOP/s
+        roof = {"kernel": "gemm_tc_kernel<BN,EPI> (%d launches per step: %s)" % (n // psteps, ", ".join(sorted(fam))),
+                "bound": "tensor", "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
+                "frac": achieved / pk["tf_sustained"],
+                "traffic": tr / tr_n if tr_n else None, "traffic_unit": "DRAM bytes per launch (ncu, profiles/traffic.json)",
                 "peak_source": pk["src"] + " (sustained bf16, kernel timed inside a long step)",
-                "avg_launch_ms": dd["ms"] / dd["n"], "flops_per_launch": dd["flops"] / dd["n"]}
+                "avg_launch_ms": fam_ms / n, "flops_per_launch": fl / n,
+                "share_of_step": fam_ms / psteps / step_ms_prof if step_ms_prof else None}
     else:
+        dd = by[other]
         achieved = dd["bytes"] / dd["ms"] / 1e6            # GB/s
-        roof = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                "frac": achieved / pk["hbm_gbs"], "traffic": traffic.get(dom), "peak_source": pk["src"],
+        roof = {"kernel": other, "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                "frac": achieved / pk["hbm_gbs"], "traffic": traffic.get(other), "peak_source": pk["src"],
                 "avg_launch_ms": dd["ms"] / dd["n"], "bytes_per_launch": dd["bytes"] / dd["n"]}
     enc_flops = flops_per_frame(bool(args.enc), T) * B * T
     whole = {"encoder_algorithmic_tflop_per_step": enc_flops / 1e12,
