@@ -1,0 +1,153 @@
+// Device-side pieces shared by the tcgen05 GEMM kernels (gemm_tc.cu: one problem per launch,
+// gemm_tc_dual.cu: two independent problems interleaved in one persistent launch).
+#pragma once
+#include "tc_common.cuh"
+
+namespace asrb {
+
+// Per epilogue group (4 warps = 128 threads = one row each): one 17 KB scratch tile that is, in
+// turn, the fp32 exchange buffer [128][33] of the fused depthwise epilogues and the staging
+// tile of the TMA store ([128][64] bf16 swizzled / [128][32] fp32 swizzled / [rows][32] bf16).
+static constexpr int GROUP_SCRATCH = 17 * 1024;
+static constexpr int XPITCH = 33;       // fp32 words per exchange-buffer row (bank-conflict-free both ways)
+
+template <int BN> struct TcCfg {
+    static constexpr int NG = BN == 256 ? 4 : 2;                       // epilogue groups (column slices)
+    static constexpr int THREADS = 64 + NG * 128;
+    static constexpr int STAGES = BN == 256 ? 3 : 5;
+    static constexpr int A_BYTES = BM * BK * 2;
+    static constexpr int B_BYTES = BN * BK * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int XCH_BYTES = NG * BM * 8 + 2 * BM * 8;         // LN partial sums per row and group + 2 peer slots (cluster LN)
+    static constexpr int SMEM = STAGES * STAGE_BYTES + NG * GROUP_SCRATCH + XCH_BYTES + 256 /*barriers + tmem slot*/;
+    static_assert((2 * STAGES + 6) * 8 + 4 <= 256, "barrier region");
+    static_assert(SMEM <= 227 * 1024, "shared memory budget");
+};
+
+// --------------------------------- fast epilogue math -----------------------------------
+__device__ __forceinline__ float act_fast(float v, int act) {
+    switch (act) {
+        case ACT_GELU: return gelu_fast(v);
+        case ACT_RELU: return fmaxf(v, 0.f);
+        case ACT_SILU: return v * sigmoid_fast(v);
+        case ACT_GELU_GELU: return gelu_fast(gelu_fast(v));
+        default: return v;
+    }
+}
+__device__ __forceinline__ void act_fast32(float (&v)[32], int act) {      // switch hoisted out of the element loop
+    switch (act) {
+        case ACT_GELU:
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = gelu_fast(v[i]);
+            break;
+        case ACT_GELU_GELU:
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = gelu_fast(gelu_fast(v[i]));
+            break;
+        case ACT_SILU:
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = v[i] * sigmoid_fast(v[i]);
+            break;
+        case ACT_RELU:
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+            break;
+        default: break;
+    }
+}
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+
+struct TcParams {
+    const float* bias; const __nv_bfloat16* res; const float* res32; float* out32; const float* gamma; const float* beta;
+    int T, K, N, taps, act, tiles_per_utt, m_tiles, n_chunks, n_out, out_f32;
+    int cluster;                 // TC_LN with N = 512: 2 CTAs own one 256-column half each and swap row sums over DSMEM
+    float eps;
+    // fused depthwise epilogue (TC_GLU_DW / TC_RES_ACT_DW): a tile's 128 rows are frames
+    // [t0 - halo, t0 + 128 - halo); rows_out = 128 - 2*halo frames are produced per tile
+    const float* dw_w; const float* dw_b; const float* pos; int kw, halo, rows_out, act2;
+};
+
+// 32 fp32 values of one row -> 32 bf16 into the swizzled staging tile (row r, columns cb..cb+31 of 64)
+__device__ __forceinline__ void stage_store32(unsigned char* staging, int r, int cb, const float (&v)[32]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int chunk = (cb >> 3) + i;                              // 16-byte chunk index 0..7 in the 128-B row
+        uint4 q;
+        q.x = pack_bf16(v[8 * i + 0], v[8 * i + 1]); q.y = pack_bf16(v[8 * i + 2], v[8 * i + 3]);
+        q.z = pack_bf16(v[8 * i + 4], v[8 * i + 5]); q.w = pack_bf16(v[8 * i + 6], v[8 * i + 7]);
+        *reinterpret_cast<uint4*>(staging + r * 128 + ((chunk ^ (r & 7)) << 4)) = q;
+    }
+}
+// 32 fp32 values of one row -> one 128-byte swizzled staging row (fp32 output tiles are 32 columns wide)
+__device__ __forceinline__ void stage_store32_f32(unsigned char* staging, int r, const float (&v)[32]) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+        *reinterpret_cast<float4*>(staging + r * 128 + ((i ^ (r & 7)) << 4)) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+}
+__device__ __forceinline__ void add_res32(float (&v)[32], const __nv_bfloat16* rp) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const uint4 q = *reinterpret_cast<const uint4*>(rp + 8 * i);
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { const float2 f = __bfloat1622float2(h[j]); v[8 * i + 2 * j] += f.x; v[8 * i + 2 * j + 1] += f.y; }
+    }
+}
+__device__ __forceinline__ void add_f32x32(float (&v)[32], const float* p) {     // plain (not read-only) loads
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { const float4 f = *(reinterpret_cast<const float4*>(p) + i); v[4 * i] += f.x; v[4 * i + 1] += f.y; v[4 * i + 2] += f.z; v[4 * i + 3] += f.w; }
+}
+__device__ __forceinline__ void store_f32x32(float* p, const float (&v)[32]) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) *(reinterpret_cast<float4*>(p) + i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+}
+__device__ __forceinline__ void add_vec32(float (&v)[32], const float* p) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { const float4 f = __ldg(reinterpret_cast<const float4*>(p) + i); v[4 * i] += f.x; v[4 * i + 1] += f.y; v[4 * i + 2] += f.z; v[4 * i + 3] += f.w; }
+}
+
+// ---- fused depthwise epilogue helpers ----------------------------------------------------
+// xbuf: [128 rows][XPITCH] fp32.  Pitch 33 makes both the row-per-thread writes (phase 1) and the
+// column-per-thread reads (phase 2) bank-conflict free, and every access is base + immediate.
+__device__ __forceinline__ void xbuf_store_row(float* xrow, const float (&v)[32]) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) xrow[i] = v[i];
+}
+
+// Phase 2: this thread owns one column and output rows [o0, o0 + OPT) of the tile (OPT = a quarter of
+// the tile's BM - KW + 1 output rows); the input row of output o and tap j is o + j.  Results stay in
+// registers (the buffer is about to be reused).
+template <int KW> struct DwSlice { static constexpr int OPT = (BM - KW + 1 + 3) / 4; };
+template <int KW>
+__device__ __forceinline__ void dw_columns(const float* xcol /* &xbuf[o0][c] */, int o0, const float* __restrict__ w,
+                                           int D, int gcol, float bias, int act2, float (&out)[32]) {
+    constexpr int OPT = DwSlice<KW>::OPT;
+    float wv[KW];
+#pragma unroll
+    for (int j = 0; j < KW; ++j) wv[j] = __ldg(w + (int64_t)j * D + gcol);
+    float win[KW];
+    const int lim = BM - o0;                                   // rows available below o0
+#pragma unroll
+    for (int j = 0; j < KW - 1; ++j) win[j + 1] = (j < lim) ? xcol[j * XPITCH] : 0.f;
+#pragma unroll
+    for (int o = 0; o < 32; ++o) {
+        if (o < OPT) {
+#pragma unroll
+            for (int j = 0; j < KW - 1; ++j) win[j] = win[j + 1];
+            win[KW - 1] = (o + KW - 1 < lim) ? xcol[(o + KW - 1) * XPITCH] : 0.f;
+            float a = bias;
+#pragma unroll
+            for (int j = 0; j < KW; ++j) a = fmaf(wv[j], win[j], a);
+            out[o] = a;
+        } else {
+            out[o] = 0.f;
+        }
+    }
+    act_fast32(out, act2);
+}
+
+
+}  // namespace asrb
