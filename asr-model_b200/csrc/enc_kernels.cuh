@@ -83,5 +83,9 @@ struct TcGemmArgs {
 bool tc_gemm_supported(int K, int N, int epilogue);
 int  tc_glu_tile_n(int N);                    // BN the GLU weight interleave must use
 int  launch_gemm_tc(const TcGemmArgs& a, cudaStream_t st);
+// channel-major variants of TC_GLU_DW / TC_RES_ACT_DW (gemm_tct.cu): lanes = channels, columns = frames
+bool tct_supported(const TcGemmArgs& a);
+int  launch_gemm_tct(const TcGemmArgs& a, cudaStream_t st);
+const __nv_bfloat16* tct_identity();          // per-device 128 x 128 identity operand (created on first use)
 
 }  // namespace asrb

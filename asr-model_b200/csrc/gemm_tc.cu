@@ -12,6 +12,7 @@
 // rows past T):  bias+act | GLU | bias+residual+act | bias(+residual)+LayerNorm over the full
 // row (the row's NB chunks of BN columns sit side by side in TMEM, <= 512 columns).
 #include "gemm_tc_epi.cuh"
+#include <cstdlib>
 
 namespace asrb {
 
@@ -68,52 +69,60 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
     if (warp == 0) {
         // ================================ TMA producer ================================
-        if (lane == 0) {
-            int s = 0; uint32_t ph = 0;
-            for (int u = u_first; u < units; u += u_step) {
-                const int m = is_ln ? u : u / p.n_chunks;
-                const int nb0 = is_ln ? (int)crank : u % p.n_chunks;
-                const int b = m / p.tiles_per_utt, t0 = (m % p.tiles_per_utt) * p.rows_out - p.halo;
-                for (int j = 0; j < nbu; ++j) {
-                    const int n0 = (nb0 + j) * BN;
-                    for (int kb = 0; kb < num_kb; ++kb) {
-                        mbar_wait(empty_bar(s), ph ^ 1);
+        // The warp runs the loop convergently (stage, phase and coordinates stay in uniform registers);
+        // one elected lane issues.
+        const bool leader = elect_one();
+        int s = 0; uint32_t ph = 0;
+        for (int u = u_first; u < units; u += u_step) {
+            const int m = is_ln ? u : u / p.n_chunks;
+            const int nb0 = is_ln ? (int)crank : u % p.n_chunks;
+            const int b = m / p.tiles_per_utt, t0 = (m % p.tiles_per_utt) * p.rows_out - p.halo;
+            for (int j = 0; j < nbu; ++j) {
+                const int n0 = (nb0 + j) * BN;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait_sleep(empty_bar(s), ph ^ 1, 32);
+                    if (leader) {
                         mbar_expect_tx(full_bar(s), C::STAGE_BYTES);
                         const int tap = kb / kb_per_tap, kc = kb - tap * kb_per_tap;
                         const uint32_t sa = smem_u32(smem + s * C::STAGE_BYTES);
                         tma_load_3d(sa, &map_a, kc * BK, t0 + tap - pad, b, full_bar(s));
                         tma_load_2d(sa + C::A_BYTES, &map_w, kb * BK, n0, full_bar(s));
-                        if (++s == STAGES) { s = 0; ph ^= 1; }
                     }
+                    __syncwarp();
+                    if (++s == STAGES) { s = 0; ph ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
         // ================================ MMA issuer ==================================
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc(BN);
-            int s = 0; uint32_t ph = 0; int it = 0;
-            for (int u = u_first; u < units; u += u_step, ++it) {
-                const int a = it % acc_stages;
-                const uint32_t aph = (uint32_t)(it / acc_stages) & 1u;
-                mbar_wait(tempty_bar(a), aph ^ 1);
-                tc_fence_after();
-                for (int j = 0; j < nbu; ++j) {
-                    const uint32_t d_tmem = tmem_base + (uint32_t)((a * nbu + j) * BN);
-                    for (int kb = 0; kb < num_kb; ++kb) {
-                        mbar_wait(full_bar(s), ph);
-                        tc_fence_after();
+        // convergent warp, one elected lane issues: the UTCHMMAs of a k-block go out back to back
+        const bool leader = elect_one();
+        constexpr uint32_t idesc = make_idesc(BN);
+        int s = 0; uint32_t ph = 0; int it = 0;
+        for (int u = u_first; u < units; u += u_step, ++it) {
+            const int a = it % acc_stages;
+            const uint32_t aph = (uint32_t)(it / acc_stages) & 1u;
+            mbar_wait_sleep(tempty_bar(a), aph ^ 1, 32);
+            tc_fence_after();
+            for (int j = 0; j < nbu; ++j) {
+                const uint32_t d_tmem = tmem_base + (uint32_t)((a * nbu + j) * BN);
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(full_bar(s), ph);
+                    tc_fence_after();
+                    if (leader) {
                         const uint32_t sa = smem_u32(smem + s * C::STAGE_BYTES);
                         const uint64_t adesc = make_smem_desc(sa), bdesc = make_smem_desc(sa + C::A_BYTES);
 #pragma unroll
                         for (int kk = 0; kk < BK / 16; ++kk)
                             tc_mma(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, (uint32_t)((kb | kk) != 0));
                         tc_commit(empty_bar(s));                              // frees the smem slot when the MMAs retire
-                        if (++s == STAGES) { s = 0; ph ^= 1; }
                     }
+                    __syncwarp();
+                    if (++s == STAGES) { s = 0; ph ^= 1; }
                 }
-                tc_commit(tfull_bar(a));                                      // accumulator complete
             }
+            if (leader) tc_commit(tfull_bar(a));                              // accumulator complete
+            __syncwarp();
         }
     } else {
         // ================================ epilogue ====================================
@@ -425,14 +434,21 @@ int tc_prepare(const TcGemmArgs& a, CUtensorMap* ma, CUtensorMap* mw, CUtensorMa
 
 int launch_gemm_tc(const TcGemmArgs& a, cudaStream_t st) {
     if (a.B <= 0 || a.T <= 0) return ASRB_OK;
+    static const char* const tags[6] = {"gemm_tc_bias_act", "gemm_tc_glu", "gemm_tc_res_act", "gemm_tc_layernorm",
+                                        "gemm_tc_glu_dw15_silu", "gemm_tc_res_gelu_dw3_gelu"};
+    static const int use_tct = [] { const char* e = getenv("ASRB_TCT"); return e ? atoi(e) : 3; }();   // dev switch: bit0 RES, bit1 GLU
+    if (((a.epilogue == TC_RES_ACT_DW && (use_tct & 1)) || (a.epilogue == TC_GLU_DW && (use_tct & 2))) && tct_supported(a)) {
+        const int no = a.epilogue == TC_GLU_DW ? a.N / 2 : a.N;
+        ProfScope ps(tags[a.epilogue], st, 2.0 * a.B * a.T * (double)a.N * a.K,
+                     2.0 * a.B * a.T * ((double)a.K + no + (a.res ? no : 0)) + 2.0 * a.N * a.K);
+        return launch_gemm_tct(a, st);
+    }
     CUtensorMap ma, mw, mo;
     TcParams p;
     int bn = 0;
     ASRB_TRY(tc_prepare(a, &ma, &mw, &mo, &p, &bn));
     const int n_out = p.n_out;
     const int units = a.epilogue == TC_LN ? p.m_tiles : p.m_tiles * p.n_chunks;
-    static const char* const tags[6] = {"gemm_tc_bias_act", "gemm_tc_glu", "gemm_tc_res_act", "gemm_tc_layernorm",
-                                        "gemm_tc_glu_dw15_silu", "gemm_tc_res_gelu_dw3_gelu"};
     ProfScope ps(tags[a.epilogue], st, 2.0 * a.B * a.T * (double)a.N * a.K * a.taps,
                  2.0 * a.B * a.T * ((double)a.K + n_out * (a.out_f32 ? 2 : 1) + (a.res ? n_out : 0)) + 2.0 * a.N * a.K * a.taps);
 #define ASRB_TC(BN_, EPI_) return launch_one<BN_, EPI_>(ma, mw, mo, p, units, st)

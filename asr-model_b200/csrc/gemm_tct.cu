@@ -1,0 +1,496 @@
+// Channel-major tcgen05 GEMMs with the depthwise convolutions of ConvLite fused into the epilogue
+// (sm_100a).  Same contraction as gemm_tc.cu with the operand roles swapped:
+//
+//   D[c, t] = sum_k W[c][k] * X[b, t, k]          (A operand = weight tile, B operand = frame tile)
+//
+// so a TMEM lane is an output CHANNEL and a TMEM column is a FRAME.  An epilogue thread therefore owns
+// one channel and reads consecutive frames straight into registers: the depthwise convolution along
+// the frames (model.py:113 k=15, model.py:146 k=3) is a sliding window over registers with per-thread
+// scalar taps -- no shared-memory transpose, no barriers, and results leave as 64-byte row segments
+// (32 consecutive channels of one frame per warp store).  Two kernels:
+//
+//   TC_RES_ACT_DW  point2 (1x1) + bias + residual + GELU -> depthwise-3 -> GELU[∘GELU] (+ sinusoids)
+//                  model.py:116-118,145-147,160-161.  256 frames per tile (1 halo frame each side).  The
+//                  residual is added by the tensor core as two extra k-blocks  I[128x128] * Y^T  (exact:
+//                  bf16 x 1.0 into the fp32 accumulator), so the epilogue issues no residual loads.
+//   TC_GLU_DW      point1 (1x1, D -> 2D) + GLU -> depthwise-15 (eval BatchNorm folded) -> SiLU
+//                  model.py:111-115.  128 frames per tile (112 produced), value and gate halves of the
+//                  same 128 channels in two accumulators (two MMAs per k-step share the frame tile).
+//
+// Roles per CTA (1 CTA / SM, persistent over (utterance, frame tile, channel tile) units):
+//   warp 0       TMA producer  (4-stage ring of 48 KB: weight box + frame box, SWIZZLE_128B)
+//   warp 1       MMA issuer    (one thread, tcgen05.mma cta_group::1 kind::f16, M = 128)
+//   warps 2..17  epilogue      (4 frame groups x 4 TMEM lane quadrants; thread = channel)
+// Accumulators: 2 x 256 TMEM columns, double-buffered across units.
+#include "gemm_tc_epi.cuh"
+#include <cstdlib>
+#include <mutex>
+#include <vector>
+
+namespace asrb {
+
+namespace {
+
+constexpr int TCT_STAGES = 4;
+constexpr int TCT_STAGE_BYTES = 48 * 1024;
+constexpr int TCT_THREADS = 64 + 16 * 32;
+constexpr int TCT_SMEM = TCT_STAGES * TCT_STAGE_BYTES + 256;
+
+template <int EPI> struct TctCfg;
+template <> struct TctCfg<TC_RES_ACT_DW> {
+    static constexpr int NF = 256, A_ROWS = 128, HALO = 1, ROWS_OUT = NF - 2;          // frames per tile / produced
+};
+template <> struct TctCfg<TC_GLU_DW> {
+    static constexpr int NF = 128, A_ROWS = 256, HALO = 8, ROWS_OUT = NF - 16;         // 7 needed each side; 8 keeps groups aligned
+};
+
+struct TctParams {
+    const float* bias; const float* dw_w; const float* dw_b; const float* pos; float* out32; __nv_bfloat16* out;
+    int T, K, n_out, tiles_per_utt, m_tiles, n_ct;
+};
+
+// erf-GELU of x given h = x / 2 (common.cuh gelu_fast with the halving folded into the producer of h):
+// gelu(x) = h + h tanh(h q'(h^2)),  q'(s) = 2 q(4 s)
+__device__ __forceinline__ float gelu_h(float h) {
+    const float s = fminf(h * h, 12.25f);
+    const float q = fmaf(fmaf(-1.148375808e-02f, s, 2.964082784e-01f), s, 1.594915636f);
+    return fmaf(h, tanh_approx(h * q), h);
+}
+template <int ACT2> __device__ __forceinline__ float act2_h(float ah) {          // act2(2 ah)
+    if (ACT2 == ACT_GELU) return gelu_h(ah);
+    if (ACT2 == ACT_GELU_GELU) return gelu_h(0.5f * gelu_h(ah));
+    return fmaf(ah, tanh_approx(ah), ah);                                        // SiLU: x sigmoid(x) = h + h tanh(h)
+}
+
+// TMEM loads without the trailing wait (several are batched before one tcgen05.wait::ld)
+__device__ __forceinline__ void tmem_ld32_nw(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld8_nw(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld4_nw(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld2_nw(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void st_bf16(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+// Taps and bias of the depthwise-3, halved (the activation that follows takes x / 2)
+struct Dw3 { float w0, w1, w2, b; };
+
+// ---- depthwise-3 over one 32-frame chunk (thread = channel).  v[] = accumulator columns S..S+31 of this
+// channel (frames tS..tS+31); (pa, pb) = the activated values of frames tS-2, tS-1.  Emits the 32 outputs of
+// frames tS-1 .. tS+30 and leaves (pa, pb) = activated frames tS+30, tS+31 for the next chunk.
+//   MASK = false: every frame of the chunk is inside [0, T) except possibly frame -1 in v[0] (zero_first), and
+//                 every output is this group's except possibly the first two (skip2);
+//   MASK = true : general warp-uniform predicates (tile touching the end of the utterance).
+// NO = n_out as a compile-time constant (store offsets become immediates) or 0. ----
+template <bool MASK, int NO, int ACT2>
+__device__ __forceinline__ void dw3_chunk(float (&v)[32], float& pa, float& pb, float hbias, const Dw3& k, const TctParams& p,
+                                          int tS, int t_lo, int t_hi, bool skip2, bool zero_first, int64_t row0 /* b*T */, int c) {
+    const int ld = NO ? NO : p.n_out;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = gelu_h(fmaf(v[i], 0.5f, hbias));      // GELU(acc + bias)   (model.py:145)
+    if (MASK) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) if (tS + i < 0 || tS + i >= p.T) v[i] = 0.f;
+    } else if (zero_first) v[0] = 0.f;                                        // frame -1: conv zero padding
+    const int64_t e0 = (row0 + tS - 1) * ld + c;                              // element of output j = 0
+    const float qa = pa, qb = pb;
+    pa = v[30]; pb = v[31];
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {                                          // two halves of 16 outputs: bounds the live registers
+        float o[16];
+#pragma unroll
+        for (int jj = 0; jj < 16; ++jj) {
+            const int j = hf * 16 + jj;
+            const float x0 = j >= 2 ? v[j >= 2 ? j - 2 : 0] : (j == 0 ? qa : qb);
+            const float x1 = j >= 1 ? v[j >= 1 ? j - 1 : 0] : qb;
+            o[jj] = act2_h<ACT2>(fmaf(k.w2, v[j], fmaf(k.w1, x1, fmaf(k.w0, x0, k.b))));
+        }
+        const int tj = tS - 1 + hf * 16;                                      // frame of o[0]
+        const int64_t eh = e0 + (int64_t)(hf * 16) * ld;
+        auto live = [&](int jj) { return MASK ? (tj + jj >= t_lo && tj + jj < t_hi) : !(skip2 && hf == 0 && jj < 2); };
+        if (p.pos) {                                                          // last block: + sinusoids (model.py:160-161)
+            const float* pp = p.pos + (int64_t)tj * ld + c;
+#pragma unroll
+            for (int jj = 0; jj < 16; ++jj) if (live(jj)) o[jj] += __ldg(pp + (int64_t)jj * ld);
+        }
+        if (p.out32) {
+#pragma unroll
+            for (int jj = 0; jj < 16; ++jj) if (live(jj)) p.out32[eh + (int64_t)jj * ld] = o[jj];
+        }
+        __nv_bfloat16* op = p.out + eh;
+#pragma unroll
+        for (int jj = 0; jj < 16; ++jj) if (live(jj)) st_bf16(op + (int64_t)jj * ld, o[jj]);
+    }
+}
+
+// ---- depthwise-15 over the 44-frame window h[] (window index i <-> frame tw + i) of one channel: emits the 28
+// outputs of frames tw + 8 .. tw + 35.  k[0..14] taps and k[15] bias, halved.  MASK: the window touches a frame
+// outside [0, T) (conv zero padding; outputs past T are dropped).  4 outputs x 2 partial sums = 8 independent
+// FFMA chains at a time. ----
+template <bool MASK, int NO, int ACT2>
+__device__ __forceinline__ void dw15_emit(float (&h)[44], const float (&k)[16], __nv_bfloat16* op, int ldr, int tw, int T) {
+    const int ld = NO ? NO : ldr;
+    if (MASK) {
+#pragma unroll
+        for (int i = 0; i < 44; ++i) if (tw + i < 0 || tw + i >= T) h[i] = 0.f;
+    }
+#pragma unroll
+    for (int j0 = 0; j0 < 28; j0 += 4) {
+        float s0[4], s1[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { s0[q] = k[15]; s1[q] = k[14] * h[j0 + q + 15]; }
+#pragma unroll
+        for (int i = 0; i < 7; ++i) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                s0[q] = fmaf(k[2 * i], h[j0 + q + 1 + 2 * i], s0[q]);
+                s1[q] = fmaf(k[2 * i + 1], h[j0 + q + 2 + 2 * i], s1[q]);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float o = act2_h<ACT2>(s0[q] + s1[q]);
+            if (!MASK || tw + 8 + j0 + q < T) st_bf16(op + (int64_t)(j0 + q) * ld, o);
+        }
+    }
+}
+
+}  // namespace
+
+template <int EPI, int NO, int ACT2>
+__global__ void __launch_bounds__(TCT_THREADS, 1)
+gemm_tct_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x,
+                const __grid_constant__ CUtensorMap map_i, const __grid_constant__ CUtensorMap map_r, const TctParams p) {
+    using C = TctCfg<EPI>;
+    constexpr bool RES = EPI == TC_RES_ACT_DW;
+    constexpr int NF = C::NF, A_BYTES = C::A_ROWS * BK * 2;
+    constexpr int STAGES = TCT_STAGES;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * TCT_STAGE_BYTES);
+    const uint32_t bar0 = smem_u32(bars);
+    auto full_bar = [&](int s) { return bar0 + 8u * s; };
+    auto empty_bar = [&](int s) { return bar0 + 8u * (STAGES + s); };
+    auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * STAGES + a); };
+    auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * STAGES + 2 + a); };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int units = p.m_tiles * p.n_ct;
+    const int kb_main = p.K / BK;
+    const int num_kb = kb_main + (RES ? 2 : 0);
+    const int ld = NO ? NO : p.n_out;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+        if (RES) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&map_i) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&map_r) : "memory");
+        }
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 16 * 32); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================================ TMA producer ================================
+        // convergent warp, one elected lane issues (keeps stage / coordinates in uniform registers)
+        const bool leader = elect_one();
+        int s = 0; uint32_t ph = 0;
+        for (int u = blockIdx.x; u < units; u += gridDim.x) {
+            const int m = u / p.n_ct, ct = u - m * p.n_ct;
+            const int b = m / p.tiles_per_utt, tb = (m - b * p.tiles_per_utt) * C::ROWS_OUT - C::HALO;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait_sleep(empty_bar(s), ph ^ 1, 64);
+                if (leader) {
+                    mbar_expect_tx(full_bar(s), TCT_STAGE_BYTES);
+                    const uint32_t sa = smem_u32(smem + s * TCT_STAGE_BYTES);
+                    if (!RES || kb < kb_main) {
+                        tma_load_2d(sa, &map_w, kb * BK, ct * C::A_ROWS, full_bar(s));
+                        tma_load_3d(sa + A_BYTES, &map_x, kb * BK, tb, b, full_bar(s));
+                    } else {                                                  // residual: I[:, 64j..] * Y[b, frames, ct*128 + 64j..]^T
+                        const int j = kb - kb_main;
+                        tma_load_2d(sa, &map_i, j * BK, 0, full_bar(s));
+                        tma_load_3d(sa + A_BYTES, &map_r, ct * 128 + j * BK, tb, b, full_bar(s));
+                    }
+                }
+                __syncwarp();
+                if (++s == STAGES) { s = 0; ph ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================ MMA issuer ==================================
+        // The whole warp runs the loop convergently (stage / phase / descriptors stay warp-uniform); one elected
+        // lane issues the MMAs and commits.
+        const bool leader = elect_one();
+        constexpr uint32_t idesc = make_idesc(NF);
+        int s = 0; uint32_t ph = 0; int it = 0;
+        for (int u = blockIdx.x; u < units; u += gridDim.x, ++it) {
+            const int a = it & 1;
+            const uint32_t aph = (uint32_t)(it >> 1) & 1u;
+            mbar_wait_sleep(tempty_bar(a), aph ^ 1, 64);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)(a * 256);
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait(full_bar(s), ph);
+                tc_fence_after();
+                const uint32_t sa = smem_u32(smem + s * TCT_STAGE_BYTES);
+                const uint64_t adesc = make_smem_desc(sa), bdesc = make_smem_desc(sa + A_BYTES);
+                if (leader) {
+                    if (RES) {
+#pragma unroll
+                        for (int kk = 0; kk < BK / 16; ++kk)
+                            tc_mma(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, (uint32_t)((kb | kk) != 0));
+                    } else {                                                  // value rows | gate rows of the same 128 channels
+                        const uint64_t gdesc = make_smem_desc(sa + 128 * BK * 2);
+#pragma unroll
+                        for (int kk = 0; kk < BK / 16; ++kk) {
+                            tc_mma(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, (uint32_t)((kb | kk) != 0));
+                            tc_mma(d_tmem + 128, gdesc + 2 * kk, bdesc + 2 * kk, idesc, (uint32_t)((kb | kk) != 0));
+                        }
+                    }
+                    tc_commit(empty_bar(s));
+                }
+                __syncwarp();
+                if (++s == STAGES) { s = 0; ph ^= 1; }
+            }
+            if (leader) tc_commit(tfull_bar(a));
+            __syncwarp();
+        }
+    } else {
+        // ================================ epilogue ====================================
+        const int ew = warp - 2;
+        const int quad = warp & 3;                         // TMEM lane quadrant this warp may read
+        const int g = ew >> 2;                             // frame group
+        const int cl = quad * 32 + lane;                   // channel inside the tile
+        // per-channel constants, halved (every activation here takes x / 2); reloaded only when the channel tile
+        // changes -- with gridDim % n_ct == 0 that is once per kernel
+        int ct_cur = -1;
+        float hb0 = 0.f, hb1 = 0.f;                        // RES: bias / 2, -            GLU: value bias / 2, gate bias / 2
+        float k[RES ? 4 : 16];                             // RES: 3 taps + bias (halved); GLU: 15 taps + bias (halved)
+        int it = 0;
+        for (int u = blockIdx.x; u < units; u += gridDim.x, ++it) {
+            const int m = u / p.n_ct, ct = u - m * p.n_ct;
+            const int b = m / p.tiles_per_utt, ft = m - b * p.tiles_per_utt;
+            const int tb = ft * C::ROWS_OUT - C::HALO;      // frame of accumulator column 0
+            const int a = it & 1;
+            const uint32_t aph = (uint32_t)(it >> 1) & 1u;
+            const int c = ct * 128 + cl;                   // output channel of this thread
+            const int64_t row0 = (int64_t)b * p.T;
+            const uint32_t acc = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(a * 256);
+            if (ct != ct_cur) {
+                ct_cur = ct;
+                constexpr int KW = RES ? 3 : 15;
+#pragma unroll
+                for (int j = 0; j < KW; ++j) k[j] = 0.5f * __ldg(p.dw_w + j * ld + c);
+                k[KW] = 0.5f * __ldg(p.dw_b + c);
+                if (RES) hb0 = 0.5f * __ldg(p.bias + c);
+                else { hb0 = 0.5f * __ldg(p.bias + ct * 256 + cl); hb1 = 0.5f * __ldg(p.bias + ct * 256 + 128 + cl); }
+            }
+
+            if constexpr (RES) {
+                Dw3 kk; kk.w0 = k[0]; kk.w1 = k[1]; kk.w2 = k[2]; kk.b = k[3];
+                // group g emits tile columns [64g - 1, 64g + 63) ∩ [1, 255): frames [t_lo, t_hi)
+                const int S0 = 64 * g;
+                const int t_lo = tb + max(S0 - 1, 1), t_hi = min(tb + S0 + 63, p.T);
+                mbar_wait_sleep(tfull_bar(a), aph, 32);
+                tc_fence_after();
+                float pa = 0.f, pb = 0.f;
+#pragma unroll 1
+                for (int ch = 0; ch < 2; ++ch) {
+                    const int S = S0 + 32 * ch, tS = tb + S;
+                    float v[32];
+                    if (ch == 0 && g > 0) {                 // activated frames tS-2, tS-1 belong to the previous group: recompute
+                        float e[2];
+                        tmem_ld2_nw(acc + S - 2, e);
+                        tmem_ld32_nw(acc + S, v);
+                        tmem_ld_wait();
+                        pa = (tS - 2 < p.T) ? gelu_h(fmaf(e[0], 0.5f, hb0)) : 0.f;
+                        pb = (tS - 1 < p.T) ? gelu_h(fmaf(e[1], 0.5f, hb0)) : 0.f;
+                    } else {
+                        tmem_ld32_nw(acc + S, v);
+                        tmem_ld_wait();
+                    }
+                    if (ch == 1) { tc_fence_before(); mbar_arrive(tempty_bar(a)); }   // last TMEM read of this unit
+                    if (tS - 1 >= p.T) continue;            // nothing left to emit (warp-uniform)
+                    if (tS + 31 < p.T)
+                        dw3_chunk<false, NO, ACT2>(v, pa, pb, hb0, kk, p, tS, t_lo, t_hi, g == 0 && ch == 0, tS < 0, row0, c);
+                    else
+                        dw3_chunk<true, NO, ACT2>(v, pa, pb, hb0, kk, p, tS, t_lo, t_hi, false, false, row0, c);
+                }
+            } else {
+                // ---- GLU -> depthwise-15 -> act2.  Group g emits tile columns [8 + 28g, 36 + 28g) from the
+                // 44-column window starting at column 28g (window index i <-> frame tw + i) ----
+                const int ws = 28 * g, tw = tb + ws;
+                float h[44];
+                mbar_wait_sleep(tfull_bar(a), aph, 32);
+                tc_fence_after();
+                {   // GLU: (v + bv) * sigmoid(g + bg) = hv + hv tanh((g + bg) / 2),  hv = (v + bv) / 2
+                    float gt[32];
+                    tmem_ld32_nw(acc + ws, h);
+                    tmem_ld32_nw(acc + 128 + ws, gt);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) { const float hv = fmaf(h[i], 0.5f, hb0); h[i] = fmaf(hv, tanh_approx(fmaf(gt[i], 0.5f, hb1)), hv); }
+                }
+                {
+                    float gt[12];
+                    tmem_ld8_nw(acc + ws + 32, h + 32);
+                    tmem_ld4_nw(acc + ws + 40, h + 40);
+                    tmem_ld8_nw(acc + 128 + ws + 32, gt);
+                    tmem_ld4_nw(acc + 128 + ws + 40, gt + 8);
+                    tmem_ld_wait();
+                    tc_fence_before();
+                    mbar_arrive(tempty_bar(a));             // accumulators drained
+#pragma unroll
+                    for (int i = 0; i < 12; ++i) { const float hv = fmaf(h[32 + i], 0.5f, hb0); h[32 + i] = fmaf(hv, tanh_approx(fmaf(gt[i], 0.5f, hb1)), hv); }
+                }
+                const int t0 = tw + 8;                      // frame of output 0 (>= 0)
+                __nv_bfloat16* op = p.out + (row0 + t0) * ld + c;
+                if (tw >= 0 && tw + 43 < p.T) dw15_emit<false, NO, ACT2>(h, k, op, ld, tw, p.T);
+                else dw15_emit<true, NO, ACT2>(h, k, op, ld, tw, p.T);
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
+// ------------------------------------ host side -------------------------------------------
+namespace {
+
+// 2-D K-major bf16 matrix [rows][cols]: box 64 x box_rows, 128-byte swizzle
+int make_mat_map(CUtensorMap* m, const void* base, int rows, int cols, int box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return fail(ASRB_E_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)base, dims, strides, box, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ASRB_E_CUDA, "cuTensorMapEncodeTiled(matrix %d x %d) -> %d", rows, cols, (int)r);
+    return ASRB_OK;
+}
+// [B][T][C] bf16 activations as the B operand: dims (C, T, B), box 64 x nf x 1, OOB -> 0
+int make_frames_map(CUtensorMap* m, const void* base, int64_t B, int64_t T, int C, int nf) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return fail(ASRB_E_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+    cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)T, (cuuint64_t)B};
+    cuuint64_t strides[2] = {(cuuint64_t)C * 2, (cuuint64_t)T * C * 2};
+    cuuint32_t box[3] = {64, (cuuint32_t)nf, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)base, dims, strides, box, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ASRB_E_CUDA, "cuTensorMapEncodeTiled(frames C=%d T=%lld B=%lld) -> %d", C, (long long)T, (long long)B, (int)r);
+    return ASRB_OK;
+}
+
+}  // namespace
+
+// 128 x 128 bf16 identity: the A operand of the residual k-blocks.  One per device, created on first use
+// (asrb_encoder_create touches it, so a captured forward never allocates).
+const __nv_bfloat16* tct_identity() {
+    static std::mutex mu;
+    static __nv_bfloat16* table[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    std::lock_guard<std::mutex> lk(mu);
+    if (!table[dev]) {
+        std::vector<__nv_bfloat16> h(128 * 128, __float2bfloat16_rn(0.f));
+        for (int i = 0; i < 128; ++i) h[i * 128 + i] = __float2bfloat16_rn(1.f);
+        void* d = nullptr;
+        if (cudaMalloc(&d, h.size() * sizeof(__nv_bfloat16)) != cudaSuccess) return nullptr;
+        if (cudaMemcpy(d, h.data(), h.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice) != cudaSuccess) { cudaFree(d); return nullptr; }
+        table[dev] = (__nv_bfloat16*)d;
+    }
+    return table[dev];
+}
+
+bool tct_supported(const TcGemmArgs& a) {
+    if (a.taps != 1 || a.K % 64 != 0 || a.out_f32 || !a.dw_w || !a.dw_b) return false;
+    if (a.epilogue == TC_RES_ACT_DW)
+        return a.N % 128 == 0 && a.dw_kw == 3 && a.res != nullptr && a.act == ACT_GELU &&
+               (a.dw_act == ACT_GELU || a.dw_act == ACT_GELU_GELU);
+    if (a.epilogue == TC_GLU_DW) return a.N % 256 == 0 && a.dw_kw == 15 && !a.pos && !a.out32 && a.dw_act == ACT_SILU;
+    return false;
+}
+
+template <int EPI, int NO, int ACT2>
+static int launch_tct(const TcGemmArgs& a, cudaStream_t st) {
+    using C = TctCfg<EPI>;
+    constexpr bool RES = EPI == TC_RES_ACT_DW;
+    const int n_out = RES ? a.N : a.N / 2;
+    CUtensorMap mw, mx, mi, mr;
+    ASRB_TRY(make_mat_map(&mw, a.W, a.N, a.K, C::A_ROWS));
+    ASRB_TRY(make_frames_map(&mx, a.A, a.B, a.T, a.K, C::NF));
+    if (RES) {
+        const __nv_bfloat16* ident = tct_identity();
+        if (!ident) return fail(ASRB_E_CUDA, "tcgen05 GEMM: identity operand unavailable");
+        ASRB_TRY(make_mat_map(&mi, ident, 128, 128, 128));
+        ASRB_TRY(make_frames_map(&mr, a.res, a.B, a.T, n_out, C::NF));
+    } else { mi = mw; mr = mx; }
+    TctParams p{};
+    p.bias = a.bias; p.dw_w = a.dw_w; p.dw_b = a.dw_b; p.pos = a.pos; p.out32 = a.out32; p.out = (__nv_bfloat16*)a.out;
+    p.T = (int)a.T; p.K = a.K; p.n_out = n_out;
+    p.tiles_per_utt = (int)((a.T + C::ROWS_OUT - 1) / C::ROWS_OUT);
+    p.m_tiles = (int)(a.B * p.tiles_per_utt);
+    p.n_ct = n_out / 128;
+    const int units = p.m_tiles * p.n_ct;
+    auto kern = gemm_tct_kernel<EPI, NO, ACT2>;
+    ASRB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TCT_SMEM));
+    const int grid = units < sm_count() ? units : sm_count();
+    kern<<<grid, TCT_THREADS, TCT_SMEM, st>>>(mw, mx, mi, mr, p);
+    ASRB_LAUNCH_CHECK();
+    return ASRB_OK;
+}
+
+int launch_gemm_tct(const TcGemmArgs& a, cudaStream_t st) {
+    if (a.epilogue == TC_RES_ACT_DW) {
+        if (a.dw_act == ACT_GELU_GELU)
+            return a.N == 512 ? launch_tct<TC_RES_ACT_DW, 512, ACT_GELU_GELU>(a, st) : launch_tct<TC_RES_ACT_DW, 0, ACT_GELU_GELU>(a, st);
+        return a.N == 512 ? launch_tct<TC_RES_ACT_DW, 512, ACT_GELU>(a, st) : launch_tct<TC_RES_ACT_DW, 0, ACT_GELU>(a, st);
+    }
+    return a.N == 1024 ? launch_tct<TC_GLU_DW, 512, ACT_SILU>(a, st) : launch_tct<TC_GLU_DW, 0, ACT_SILU>(a, st);
+}
+
+}  // namespace asrb

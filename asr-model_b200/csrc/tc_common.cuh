@@ -29,6 +29,24 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "bra WAIT_LOOP;\n\t"
         "WAIT_DONE:\n\t}" ::"r"(bar), "r"(parity) : "memory");
 }
+// spin on an mbarrier with a short sleep between probes: the waiting warp stops competing for issue slots
+// with the epilogue warps that share its scheduler
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity, uint32_t ns) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAITS_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAITS_DONE;\n\t"
+        "nanosleep.u32 %2;\n\t"
+        "bra WAITS_LOOP;\n\t"
+        "WAITS_DONE:\n\t}" ::"r"(bar), "r"(parity), "r"(ns) : "memory");
+}
+
+__device__ __forceinline__ bool elect_one() {          // true in exactly one lane of a converged warp
+    uint32_t pred = 0;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
                  ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
