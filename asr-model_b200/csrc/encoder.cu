@@ -320,23 +320,19 @@ int encoder_body(asrb_encoder* e, const EncBuffers& w, const float* x_c1, int in
             TcGemmArgs h{};
             h.A = (const __nv_bfloat16*)w.U; h.W = lw.w2_h; h.bias = lw.b2; h.res = (const __nv_bfloat16*)w.Y;
             h.B = B; h.T = T; h.K = D; h.N = D; h.taps = 1; h.act = ACT_GELU;
-            if (tc_gemm_supported(D, D, TC_RES_ACT_DW)) {
-                // point2 + residual + GELU + depthwise-3 + GELU (+ next block's GELU | + sinusoids): U, Y -> X
-                const bool to_out = last && !e->cfg.enc && out_dtype == ASRB_BF16;
-                h.epilogue = TC_RES_ACT_DW; h.out = to_out ? out : w.X;
-                h.dw_w = lw.dw3; h.dw_b = lw.dw3_b; h.dw_kw = 3; h.dw_act = last ? ACT_GELU : ACT_GELU_GELU;
-                h.pos = last ? w.pos : nullptr;
-                h.out32 = (last && e->cfg.enc && tc_gemm_supported(D, D, TC_LN)) ? (float*)w.G : nullptr;
-                ASRB_TRY(launch_gemm_tc(h, st));
-                if (last && !e->cfg.enc && out_dtype != ASRB_BF16) {
-                    ProfScope ps("convert", st, 0.0, 6.0 * rows * D);
-                    convert_kernel<<<148 * 8, 256, 0, st>>>((const __nv_bfloat16*)w.X, (float*)out, rows * D);
-                    ASRB_LAUNCH_CHECK();
-                }
-                continue;
-            }
-            h.epilogue = TC_RES_ACT; h.out = w.H; h.out_f32 = 1;
+            // point2 + residual + GELU + depthwise-3 + GELU (+ next block's GELU | + sinusoids): U, Y -> X
+            const bool to_out = last && !e->cfg.enc && out_dtype == ASRB_BF16;
+            h.epilogue = TC_RES_ACT_DW; h.out = to_out ? out : w.X;
+            h.dw_w = lw.dw3; h.dw_b = lw.dw3_b; h.dw_kw = 3; h.dw_act = last ? ACT_GELU : ACT_GELU_GELU;
+            h.pos = last ? w.pos : nullptr;
+            h.out32 = (last && e->cfg.enc && tc_gemm_supported(D, D, TC_LN)) ? (float*)w.G : nullptr;
             ASRB_TRY(launch_gemm_tc(h, st));
+            if (last && !e->cfg.enc && out_dtype != ASRB_BF16) {
+                ProfScope ps("convert", st, 0.0, 6.0 * rows * D);
+                convert_kernel<<<148 * 8, 256, 0, st>>>((const __nv_bfloat16*)w.X, (float*)out, rows * D);
+                ASRB_LAUNCH_CHECK();
+            }
+            continue;
         } else {
             ASRB_TRY(launch_gemm_simt(w.X, DT_F32, lw.wc_f, lw.bc, nullptr, w.H, DT_F32, B, T, D, D, 3, ACT_NONE, st));
             ASRB_TRY(launch_layernorm(w.H, nullptr, lw.gamma, lw.beta, w.Y, DT_F32, rows, D, 1e-5f, st));

@@ -5,14 +5,16 @@
 // A is channels-last bf16 [B][T][K]; a 3-D TMA map (K, T, B) with OOB zero fill supplies the
 // conv halo (t = -1, t = T) and the ragged last tile of every utterance for free.  W is
 // bf16 [N][taps*K], K-major.  Accumulators live in TMEM (fp32).  Roles per CTA (1 CTA / SM):
-//   warp 0      TMA producer   (A box 64x128, W box 64xBN, SWIZZLE_128B, 4-6 stage ring)
-//   warp 1      MMA issuer     (one thread: tcgen05.mma cta_group::1 kind::f16, M=128, N=BN)
-//   warps 2..9  epilogue       (two column halves x four TMEM lane quadrants; thread = row)
+//   warp 0      TMA producer   (A box 64x128, W box 64xBN, SWIZZLE_128B, 3-5 stage ring)
+//   warp 1      MMA issuer     (tcgen05.mma cta_group::1 kind::f16, M=128, N=BN)
+//               both run their loops convergently with one elected lane issuing, so stage, phase and
+//               descriptors stay in uniform registers and the UTCHMMAs of a k-block go out back to back
+//   warps 2..   epilogue       (BN/64 column groups x four TMEM lane quadrants; thread = row)
 // Epilogues (fp32 math, bf16 store through swizzled smem + TMA store, which also clips the
-// rows past T):  bias+act | GLU | bias+residual+act | bias(+residual)+LayerNorm over the full
-// row (the row's NB chunks of BN columns sit side by side in TMEM, <= 512 columns).
+// rows past T):  bias+act | bias+residual+act | bias(+residual)+LayerNorm over the full row (N <= 512:
+// a CTA pair owns one 256-column half each and swaps row sums over DSMEM).  The two epilogues with a
+// fused depthwise convolution (TC_GLU_DW, TC_RES_ACT_DW) live in gemm_tct.cu (lanes = channels).
 #include "gemm_tc_epi.cuh"
-#include <cstdlib>
 
 namespace asrb {
 
@@ -212,72 +214,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         if (leader) { tma_store_3d(&map_out, stg_u32, gbase + c - 32, t0, b); tma_commit(); }
                     }
                 }
-            } else if (EPI == TC_GLU_DW || EPI == TC_RES_ACT_DW) {
-                // phase 1 (thread = row): accumulator -> bias (+GLU | +residual, act) -> xbuf (fp32)
-                // phase 2 (thread = column x 32-row slice): depthwise conv down the tile rows + act2
-                //          (+ sinusoids) -> registers -> bf16 tile [rows_out][32] -> TMA store
-                constexpr bool GLU = EPI == TC_GLU_DW;
-                constexpr int OUT_PER_TILE = GLU ? BN / 2 : BN;
-                constexpr int COLS = OUT_PER_TILE / NG;                       // per group
-                float* xbuf = reinterpret_cast<float*>(stg);
-                const int slice = ew & 3;                                     // phase-2 row slice of this warp
-                for (int cc = 0; cc < COLS; cc += 32) {
-                    const int tc0 = group * COLS + cc;                        // column inside the accumulator
-                    const int gc = nb0 * OUT_PER_TILE + tc0;                  // global output column of this chunk
-                    float v[32];
-                    tmem_ld32(acc + tc0, v);
-                    if (GLU) {
-                        float gt[32];
-                        tmem_ld32(acc + BN / 2 + tc0, gt);
-                        const int vb = nb0 * BN + tc0;
-                        add_vec32(v, p.bias + vb);
-                        add_vec32(gt, p.bias + vb + BN / 2);
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) v[i] *= sigmoid_fast(gt[i]);
-                    } else {
-                        add_vec32(v, p.bias + gc);
-                        if (row_ok) add_res32(v, p.res + grow * p.n_out + gc);
-                        act_fast32(v, p.act);
-                    }
-                    if (!row_ok) {                                            // conv zero padding outside [0, T)
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) v[i] = 0.f;
-                    }
-                    if (leader) tma_wait_read0();                             // previous TMA store has read the tile
-                    epi_bar(bar_id, 128);
-                    xbuf_store_row(xbuf + r * XPITCH, v);
-                    epi_bar(bar_id, 128);
-                    float o[32];
-                    const int gcol = gc + lane;
-                    const float dwb = __ldg(p.dw_b + gcol);
-                    const int opt = p.kw == 15 ? DwSlice<15>::OPT : DwSlice<3>::OPT;   // outputs per thread
-                    const int o0 = slice * opt;
-                    const float* xcol = xbuf + o0 * XPITCH + lane;
-                    const int tout0 = t0 + p.halo + o0;                       // frame of this thread's first output row
-                    const int nrow = min(min(opt, p.rows_out - o0), p.T - tout0);   // valid outputs of this thread
-                    if (p.pos) {                                              // last block: + sinusoids; loads issued before the taps
-                        float pv[32];
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) pv[i] = (i < nrow) ? __ldg(p.pos + (int64_t)(tout0 + i) * p.n_out + gcol) : 0.f;
-                        dw_columns<3>(xcol, o0, p.dw_w, p.n_out, gcol, dwb, p.act2, o);
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) o[i] += pv[i];
-                    } else if (p.kw == 15) dw_columns<15>(xcol, o0, p.dw_w, p.n_out, gcol, dwb, p.act2, o);
-                    else dw_columns<3>(xcol, o0, p.dw_w, p.n_out, gcol, dwb, p.act2, o);
-                    if (p.out32) {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i)
-                            if (i < nrow) p.out32[((int64_t)b * p.T + tout0 + i) * p.n_out + gcol] = o[i];
-                    }
-                    epi_bar(bar_id, 128);                                     // everyone is done reading xbuf
-                    __nv_bfloat16* tile = reinterpret_cast<__nv_bfloat16*>(stg) + o0 * 32 + lane;   // [rows_out][32] bf16
-#pragma unroll
-                    for (int i = 0; i < 32; ++i)
-                        if (i < opt && o0 + i < p.rows_out) tile[i * 32] = __float2bfloat16_rn(o[i]);
-                    fence_async_smem();
-                    epi_bar(bar_id, 128);
-                    if (leader) { tma_store_3d(&map_out, stg_u32, gc, t0 + p.halo, b); tma_commit(); }
-                }
             } else {
                 // ---- bias (+ residual) + activation; 64 output columns per group ----
                 constexpr int COLS = BN / NG;
@@ -338,20 +274,6 @@ static int make_out_f32_map(CUtensorMap* m, const void* base, int64_t B, int64_t
     if (r != CUDA_SUCCESS) return fail(ASRB_E_CUDA, "cuTensorMapEncodeTiled(fp32 out C=%d) -> %d", C, (int)r);
     return ASRB_OK;
 }
-// bf16 output of the fused depthwise epilogues: box 32 cols x rows_out frames, plain 64-byte rows
-static int make_dw_out_map(CUtensorMap* m, const void* base, int64_t B, int64_t T, int C, int rows_out) {
-    EncodeTiledFn fn = encode_fn();
-    if (!fn) return fail(ASRB_E_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
-    cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)T, (cuuint64_t)B};
-    cuuint64_t strides[2] = {(cuuint64_t)C * 2, (cuuint64_t)T * C * 2};
-    cuuint32_t box[3] = {32, (cuuint32_t)rows_out, 1};
-    cuuint32_t es[3] = {1, 1, 1};
-    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)base, dims, strides, box, es,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return fail(ASRB_E_CUDA, "cuTensorMapEncodeTiled(dw out C=%d rows=%d) -> %d", C, rows_out, (int)r);
-    return ASRB_OK;
-}
 static int make_w_map(CUtensorMap* m, const void* base, int N, int Ktot, int bn) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return fail(ASRB_E_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
@@ -367,7 +289,6 @@ static int make_w_map(CUtensorMap* m, const void* base, int N, int Ktot, int bn)
 }
 
 static int pick_bn(int N, int epi) {
-    if (epi == TC_GLU_DW || epi == TC_RES_ACT_DW) return 256;
     if (epi == TC_LN) return (N % 256 == 0) ? 256 : 128;
     return (N % 256 == 0) ? 256 : 128;
 }
@@ -376,7 +297,8 @@ int tc_glu_tile_n(int) { return 256; }
 bool tc_gemm_supported(int K, int N, int epi) {
     if (K % 64 != 0 || N % 128 != 0) return false;
     if (epi == TC_GLU) return false;                 // superseded by TC_GLU_DW
-    if ((epi == TC_GLU_DW || epi == TC_RES_ACT_DW) && N % 256 != 0) return false;
+    if (epi == TC_GLU_DW) return N % 256 == 0;       // channel-major kernels (gemm_tct.cu)
+    if (epi == TC_RES_ACT_DW) return true;
     if (epi == TC_LN && N > 512) return false;
     return true;
 }
@@ -406,24 +328,20 @@ int tc_prepare(const TcGemmArgs& a, CUtensorMap* ma, CUtensorMap* mw, CUtensorMa
     if (!tc_gemm_supported(a.K, a.N, a.epilogue))
         return fail(ASRB_E_ARG, "tcgen05 GEMM: unsupported shape K=%d N=%d epilogue=%d", a.K, a.N, a.epilogue);
     const int bn = pick_bn(a.N, a.epilogue);
-    const bool glu = a.epilogue == TC_GLU || a.epilogue == TC_GLU_DW;
-    const bool dw = a.epilogue == TC_GLU_DW || a.epilogue == TC_RES_ACT_DW;
-    const int n_out = glu ? a.N / 2 : a.N;
-    if (dw && ((a.dw_kw != 3 && a.dw_kw != 15) || !a.dw_w || !a.dw_b || a.out_f32 || a.taps != 1 || (a.pos && a.dw_kw != 3)))
-        return fail(ASRB_E_ARG, "tcgen05 GEMM: bad fused-depthwise arguments");
-    if (a.epilogue == TC_RES_ACT_DW && !a.res) return fail(ASRB_E_ARG, "tcgen05 GEMM: residual required");
-    const int halo = dw ? a.dw_kw / 2 : 0, rows_out = BM - 2 * halo;
+    if (a.epilogue == TC_GLU_DW || a.epilogue == TC_RES_ACT_DW)
+        return fail(ASRB_E_ARG, "tcgen05 GEMM: fused-depthwise epilogue %d with act=%d dw_act=%d kw=%d is not built", a.epilogue, a.act, a.dw_act, a.dw_kw);
+    const int n_out = a.N;
+    const int halo = 0, rows_out = BM;
     ASRB_TRY(make_act_map(ma, a.A, a.B, a.T, a.K));
     ASRB_TRY(make_w_map(mw, a.W, a.N, a.taps * a.K, bn));
-    if ((a.res32 || (a.out32 && !dw)) && a.epilogue != TC_LN) return fail(ASRB_E_ARG, "tcgen05 GEMM: fp32 residual streams are a LayerNorm-epilogue feature");
+    if ((a.res32 || a.out32) && a.epilogue != TC_LN) return fail(ASRB_E_ARG, "tcgen05 GEMM: fp32 residual streams are a LayerNorm-epilogue feature");
     if (a.out_f32 && a.epilogue == TC_LN) return fail(ASRB_E_ARG, "tcgen05 GEMM: LayerNorm epilogue stores bf16 only");
-    if (dw) ASRB_TRY(make_dw_out_map(mo, a.out, a.B, a.T, n_out, rows_out));
-    else if (a.out_f32) ASRB_TRY(make_out_f32_map(mo, a.out, a.B, a.T, n_out));
+    if (a.out_f32) ASRB_TRY(make_out_f32_map(mo, a.out, a.B, a.T, n_out));
     else ASRB_TRY(make_act_map(mo, a.out, a.B, a.T, n_out));
     TcParams& p = *pp;
     p.bias = a.bias; p.res = a.res; p.res32 = a.res32; p.out32 = a.out32; p.gamma = a.gamma; p.beta = a.beta;
     p.T = (int)a.T; p.K = a.K; p.N = a.N; p.taps = a.taps; p.act = a.act;
-    p.dw_w = a.dw_w; p.dw_b = a.dw_b; p.pos = a.pos; p.kw = a.dw_kw; p.halo = halo; p.rows_out = rows_out; p.act2 = a.dw_act;
+    p.halo = halo; p.rows_out = rows_out;
     p.tiles_per_utt = (int)((a.T + rows_out - 1) / rows_out);
     p.m_tiles = (int)(a.B * p.tiles_per_utt);
     p.n_chunks = a.N / bn; p.n_out = n_out; p.eps = a.eps; p.out_f32 = a.out_f32;
@@ -436,8 +354,7 @@ int launch_gemm_tc(const TcGemmArgs& a, cudaStream_t st) {
     if (a.B <= 0 || a.T <= 0) return ASRB_OK;
     static const char* const tags[6] = {"gemm_tc_bias_act", "gemm_tc_glu", "gemm_tc_res_act", "gemm_tc_layernorm",
                                         "gemm_tc_glu_dw15_silu", "gemm_tc_res_gelu_dw3_gelu"};
-    static const int use_tct = [] { const char* e = getenv("ASRB_TCT"); return e ? atoi(e) : 3; }();   // dev switch: bit0 RES, bit1 GLU
-    if (((a.epilogue == TC_RES_ACT_DW && (use_tct & 1)) || (a.epilogue == TC_GLU_DW && (use_tct & 2))) && tct_supported(a)) {
+    if ((a.epilogue == TC_RES_ACT_DW || a.epilogue == TC_GLU_DW) && tct_supported(a)) {   // channel-major kernels (gemm_tct.cu)
         const int no = a.epilogue == TC_GLU_DW ? a.N / 2 : a.N;
         ProfScope ps(tags[a.epilogue], st, 2.0 * a.B * a.T * (double)a.N * a.K,
                      2.0 * a.B * a.T * ((double)a.K + no + (a.res ? no : 0)) + 2.0 * a.N * a.K);
@@ -457,8 +374,6 @@ int launch_gemm_tc(const TcGemmArgs& a, cudaStream_t st) {
             case TC_BIAS_ACT: ASRB_TC(256, TC_BIAS_ACT);
             case TC_RES_ACT: ASRB_TC(256, TC_RES_ACT);
             case TC_LN: ASRB_TC(256, TC_LN);
-            case TC_GLU_DW: ASRB_TC(256, TC_GLU_DW);
-            case TC_RES_ACT_DW: ASRB_TC(256, TC_RES_ACT_DW);
         }
     } else {
         switch (a.epilogue) {

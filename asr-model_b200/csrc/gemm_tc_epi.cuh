@@ -1,15 +1,13 @@
-// Device-side pieces shared by the tcgen05 GEMM kernels (gemm_tc.cu: one problem per launch,
-// gemm_tc_dual.cu: two independent problems interleaved in one persistent launch).
+// Device-side pieces shared by the tcgen05 GEMM kernels (gemm_tc.cu: lanes = frames; gemm_tct.cu: lanes =
+// channels, with the depthwise convolutions fused).
 #pragma once
 #include "tc_common.cuh"
 
 namespace asrb {
 
-// Per epilogue group (4 warps = 128 threads = one row each): one 17 KB scratch tile that is, in
-// turn, the fp32 exchange buffer [128][33] of the fused depthwise epilogues and the staging
-// tile of the TMA store ([128][64] bf16 swizzled / [128][32] fp32 swizzled / [rows][32] bf16).
-static constexpr int GROUP_SCRATCH = 17 * 1024;
-static constexpr int XPITCH = 33;       // fp32 words per exchange-buffer row (bank-conflict-free both ways)
+// Per epilogue group (4 warps = 128 threads = one row each): the 16 KB staging tile of the TMA store
+// ([128][64] bf16 swizzled / [128][32] fp32 swizzled).
+static constexpr int GROUP_SCRATCH = 16 * 1024;
 
 template <int BN> struct TcCfg {
     static constexpr int NG = BN == 256 ? 4 : 2;                       // epilogue groups (column slices)
@@ -65,9 +63,7 @@ struct TcParams {
     int T, K, N, taps, act, tiles_per_utt, m_tiles, n_chunks, n_out, out_f32;
     int cluster;                 // TC_LN with N = 512: 2 CTAs own one 256-column half each and swap row sums over DSMEM
     float eps;
-    // fused depthwise epilogue (TC_GLU_DW / TC_RES_ACT_DW): a tile's 128 rows are frames
-    // [t0 - halo, t0 + 128 - halo); rows_out = 128 - 2*halo frames are produced per tile
-    const float* dw_w; const float* dw_b; const float* pos; int kw, halo, rows_out, act2;
+    int halo, rows_out;          // rows_out = 128 frames per tile, halo = 0 (kept for the tile arithmetic)
 };
 
 // 32 fp32 values of one row -> 32 bf16 into the swizzled staging tile (row r, columns cb..cb+31 of 64)
@@ -108,46 +104,5 @@ __device__ __forceinline__ void add_vec32(float (&v)[32], const float* p) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) { const float4 f = __ldg(reinterpret_cast<const float4*>(p) + i); v[4 * i] += f.x; v[4 * i + 1] += f.y; v[4 * i + 2] += f.z; v[4 * i + 3] += f.w; }
 }
-
-// ---- fused depthwise epilogue helpers ----------------------------------------------------
-// xbuf: [128 rows][XPITCH] fp32.  Pitch 33 makes both the row-per-thread writes (phase 1) and the
-// column-per-thread reads (phase 2) bank-conflict free, and every access is base + immediate.
-__device__ __forceinline__ void xbuf_store_row(float* xrow, const float (&v)[32]) {
-#pragma unroll
-    for (int i = 0; i < 32; ++i) xrow[i] = v[i];
-}
-
-// Phase 2: this thread owns one column and output rows [o0, o0 + OPT) of the tile (OPT = a quarter of
-// the tile's BM - KW + 1 output rows); the input row of output o and tap j is o + j.  Results stay in
-// registers (the buffer is about to be reused).
-template <int KW> struct DwSlice { static constexpr int OPT = (BM - KW + 1 + 3) / 4; };
-template <int KW>
-__device__ __forceinline__ void dw_columns(const float* xcol /* &xbuf[o0][c] */, int o0, const float* __restrict__ w,
-                                           int D, int gcol, float bias, int act2, float (&out)[32]) {
-    constexpr int OPT = DwSlice<KW>::OPT;
-    float wv[KW];
-#pragma unroll
-    for (int j = 0; j < KW; ++j) wv[j] = __ldg(w + (int64_t)j * D + gcol);
-    float win[KW];
-    const int lim = BM - o0;                                   // rows available below o0
-#pragma unroll
-    for (int j = 0; j < KW - 1; ++j) win[j + 1] = (j < lim) ? xcol[j * XPITCH] : 0.f;
-#pragma unroll
-    for (int o = 0; o < 32; ++o) {
-        if (o < OPT) {
-#pragma unroll
-            for (int j = 0; j < KW - 1; ++j) win[j] = win[j + 1];
-            win[KW - 1] = (o + KW - 1 < lim) ? xcol[(o + KW - 1) * XPITCH] : 0.f;
-            float a = bias;
-#pragma unroll
-            for (int j = 0; j < KW; ++j) a = fmaf(wv[j], win[j], a);
-            out[o] = a;
-        } else {
-            out[o] = 0.f;
-        }
-    }
-    act_fast32(out, act2);
-}
-
 
 }  // namespace asrb
