@@ -485,12 +485,13 @@ static int launch_tct(const TcGemmArgs& a, cudaStream_t st) {
 }
 
 int launch_gemm_tct(const TcGemmArgs& a, cudaStream_t st) {
-    if (a.epilogue == TC_RES_ACT_DW) {
-        if (a.dw_act == ACT_GELU_GELU)
-            return a.N == 512 ? launch_tct<TC_RES_ACT_DW, 512, ACT_GELU_GELU>(a, st) : launch_tct<TC_RES_ACT_DW, 0, ACT_GELU_GELU>(a, st);
-        return a.N == 512 ? launch_tct<TC_RES_ACT_DW, 512, ACT_GELU>(a, st) : launch_tct<TC_RES_ACT_DW, 0, ACT_GELU>(a, st);
-    }
-    return a.N == 1024 ? launch_tct<TC_GLU_DW, 512, ACT_SILU>(a, st) : launch_tct<TC_GLU_DW, 0, ACT_SILU>(a, st);
+    // n_out as a compile-time constant for the encoder widths of BASELINE.json (512, 1024); generic otherwise
+#define ASRB_TCT(EPI_, ACT_, no) \
+    ((no) == 512 ? launch_tct<EPI_, 512, ACT_>(a, st) : (no) == 1024 ? launch_tct<EPI_, 1024, ACT_>(a, st) : launch_tct<EPI_, 0, ACT_>(a, st))
+    if (a.epilogue == TC_RES_ACT_DW)
+        return a.dw_act == ACT_GELU_GELU ? ASRB_TCT(TC_RES_ACT_DW, ACT_GELU_GELU, a.N) : ASRB_TCT(TC_RES_ACT_DW, ACT_GELU, a.N);
+    return ASRB_TCT(TC_GLU_DW, ACT_SILU, a.N / 2);
+#undef ASRB_TCT
 }
 
 }  // namespace asrb

@@ -56,6 +56,63 @@ def gather_outputs(local: torch.Tensor, total: int, group=None, out: Optional[to
     return out, None
 
 
+class PeerExchange:
+    """Gathered ``[total, T, D]`` tensors in symmetric memory (torch.distributed._symmetric_memory: every
+    rank maps every peer's copy over NVLink / NVSwitch).  A rank PUSHES its block into each peer's copy with
+    ``cudaMemcpyAsync`` on a side stream, i.e. on the copy engines: no SM is taken from the persistent
+    tensor-core kernels of the next step, which is what an NCCL send/recv kernel cannot do when every SM
+    is occupied (measured at 8 x B200: 6.3 ms per step with NCCL point-to-point against 3.0 ms of compute).
+    A device-side barrier on the signal pads closes each step's exchange.  ``slots`` gathered tensors are
+    cycled so that a peer running one step ahead never writes into a tensor the consumer may still read."""
+
+    def __init__(self, total: int, T: int, D: int, dtype, device, group=None, slots: int = 3):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        self.shape, self.dtype = (total, T, D), dtype
+        self.bufs, self.hdls, self.peers = [], [], []
+        for _ in range(slots):
+            t = symm_mem.empty(total, T, D, dtype=dtype, device=device)
+            h = symm_mem.rendezvous(t, self.group)
+            self.bufs.append(t)
+            self.hdls.append(h)
+            self.peers.append([h.get_buffer(r, self.shape, dtype) if r != self.rank else t for r in range(self.world)])
+        self.stream = torch.cuda.Stream(device)
+        self.step = 0
+
+    def next_slot(self) -> int:
+        k = self.step % len(self.bufs)
+        self.step += 1
+        return k
+
+    def push(self, slot: int, lo: int, hi: int):
+        """Rows [lo, hi) of this rank's copy were produced on the current stream: send them to every peer."""
+        ev = torch.cuda.Event()
+        ev.record()
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(ev)
+            src = self.bufs[slot][lo:hi]
+            for k in range(1, self.world):                      # staggered so the peers' ingress ports are used evenly
+                r = (self.rank + k) % self.world
+                self.peers[slot][r][lo:hi].copy_(src, non_blocking=True)
+
+    def close(self, slot: int) -> torch.cuda.Event:
+        """All ranks' pushes of this step have landed once the returned event has completed."""
+        with torch.cuda.stream(self.stream):
+            self.hdls[slot].barrier(channel=slot)
+            done = torch.cuda.Event()
+            done.record(self.stream)
+        return done
+
+
+class _EventWork:                       # the same .wait() surface as a c10d Work
+    def __init__(self, ev):
+        self.ev = ev
+
+    def wait(self):
+        torch.cuda.current_stream().wait_event(self.ev)
+
+
 class ShardedEncoder:
     """Runs ``compute(wave_shard[, out=]) -> [n, T, D]`` on this rank's utterances and gathers.
 
@@ -69,7 +126,7 @@ class ShardedEncoder:
 
     def __init__(self, compute: Callable[..., torch.Tensor], group=None, micro: int = 0, gather: bool = True,
                  shape_of: Optional[Callable[[torch.Tensor], Tuple[int, int, torch.dtype]]] = None,
-                 overlap_steps: bool = False):
+                 overlap_steps: bool = False, exchange: str = "auto"):
         """``overlap_steps``: do not wait for a call's exchange before returning; it is waited for at the
         end of the NEXT call (or by ``finish()``), so the gather of step i rides under the compute of
         step i+1.  The local block of the returned tensor is always valid on the current stream; the
@@ -77,6 +134,27 @@ class ShardedEncoder:
         self.compute, self.group, self.micro, self.gather, self.shape_of = compute, group, micro, gather, shape_of
         self.overlap_steps = overlap_steps
         self._inflight = []
+        # "peer": copy-engine pushes through symmetric memory (PeerExchange); "nccl": grouped send/recv;
+        # "auto": peer on the NCCL backend when shape_of is known and the rendezvous succeeds, else nccl
+        self.exchange = exchange
+        self._peer: Optional[PeerExchange] = None
+        self._peer_key = None
+
+    def _peer_exchange(self, total, T, D, dt, device) -> Optional[PeerExchange]:
+        if self.exchange == "nccl" or device.type != "cuda" or dist.get_backend(self.group) != "nccl":
+            return None
+        key = (total, T, D, dt)
+        if self._peer is None or self._peer_key != key:
+            try:
+                self.finish()
+                self._peer = PeerExchange(total, T, D, dt, device, self.group)
+                self._peer_key = key
+            except Exception:
+                if self.exchange == "peer":
+                    raise
+                self.exchange = "nccl"               # no symmetric memory on this system: NCCL point-to-point
+                return None
+        return self._peer
 
     def finish(self):
         for w in self._inflight:
@@ -108,6 +186,23 @@ class ShardedEncoder:
         if total % world != 0:
             local = torch.cat([self._run(waves[s:e]) for s, e in micro_batches(0, n_local, self.micro)])
             return gather_outputs(local, total, self.group)[0]
+        if self.shape_of is not None:
+            T, D, dt = self.shape_of(waves)
+            px = self._peer_exchange(total, T, D, dt, waves.device)
+            if px is not None:
+                slot = px.next_slot()
+                out = px.bufs[slot]
+                for s, e in micro_batches(0, n_local, self.micro):
+                    self._run(waves[s:e], out=out[lo + s: lo + e])
+                    px.push(slot, lo + s, lo + e)
+                work = _EventWork(px.close(slot))
+                if self.overlap_steps:
+                    prev, self._inflight = self._inflight, [work]
+                    for w in prev:
+                        w.wait()
+                else:
+                    work.wait()
+                return out
         out = None
         pending = []
         for s, e in micro_batches(0, n_local, self.micro):
