@@ -456,6 +456,12 @@ extern "C" int asrb_pcm_to_hidden(const asrb_logmel_plan* pl, asrb_encoder* e, c
     uint32_t* keys = tail.take<uint32_t>((size_t)B);
     if (!w.ok || !tail.ok()) return fail(ASRB_E_WORKSPACE, "asrb_pcm_to_hidden: workspace carve failed");
     const bool bf = e->cfg.compute == ASRB_BF16;
+    if (bf && !logmel_out) {
+        // the front end writes the stem GEMM's operand itself (bf16 channels-last) and the floor runs in place
+        ASRB_TRY(logmel_pass1(pl, pcm, B, n_samples, pcm_stride, lengths, nullptr, keys, st, (__nv_bfloat16*)w.a0, e->CP));
+        ASRB_TRY(logmel_floor_cl(pl, (__nv_bfloat16*)w.a0, e->CP, keys, lengths, B, n_samples, st));
+        return encoder_body(e, w, nullptr, pl->n_mels, B, T, out, out_dtype, st);
+    }
     ASRB_TRY(logmel_pass1(pl, pcm, B, n_samples, pcm_stride, lengths, mel, keys, st));
     // the dynamic-range floor (essentials.py:489) is applied while changing layout for conv1
     ASRB_TRY(launch_to_channels_last(mel, w.a0, bf ? DT_BF16 : DT_F32, B, pl->n_mels, bf ? e->CP : pl->n_mels, T,

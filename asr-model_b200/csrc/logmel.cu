@@ -28,7 +28,9 @@ struct LogmelParams {
     const int* mel_lo;         // [M] first bin of filter m
     const int* mel_cnt;        // [M] taps (0 for an all-zero filter)
     const float* mel_w;        // [M][kmax]
-    float* out;                // [B][M][T]
+    float* out;                // [B][M][T] fp32 (reference layout), or NULL with out_cl set
+    __nv_bfloat16* out_cl;     // fused path: [B][T][CP] bf16 channels-last, channels >= M zero (the stem GEMM's operand)
+    int CP;
     uint32_t* keys;            // [B]
 };
 
@@ -72,6 +74,10 @@ logmel_kernel(const LogmelParams p, int tiles_per_utt, int total_tiles) {
     float*  s_melw = reinterpret_cast<float*>(s_y + C::GROUPS * C::YSTRIDE);   // [M][kmax]
     int*    s_lo  = reinterpret_cast<int*>(s_melw + p.M * p.kmax);      // [M]
     int*    s_cnt = s_lo + p.M;                                         // [M]
+    // fused path: the tile's [FB][CP] bf16 output is transposed through shared memory (pitch CP + 2 halves:
+    // frame-per-lane writes and row reads are both conflict free)
+    __nv_bfloat16* s_cl = reinterpret_cast<__nv_bfloat16*>(s_cnt + p.M + (p.M & 1));
+    const int clp = p.CP + 2;
     __shared__ float s_red[32];
 
     const int tid = threadIdx.x;
@@ -108,6 +114,7 @@ logmel_kernel(const LogmelParams p, int tiles_per_utt, int total_tiles) {
     for (int i = tid; i < R * R; i += C::THREADS) s_tw[i] = p.twiddle[i];
     for (int i = tid; i < p.M * p.kmax; i += C::THREADS) s_melw[i] = p.mel_w[i];
     for (int i = tid; i < p.M; i += C::THREADS) { s_lo[i] = p.mel_lo[i]; s_cnt[i] = p.mel_cnt[i]; }
+    if (p.out_cl) for (int i = tid; i < FB * clp; i += C::THREADS) s_cl[i] = __float2bfloat16_rn(0.f);   // channels >= M stay 0
 
     const int g = tid / R, j = tid - g * R;
     float2* yg = s_y + g * C::YSTRIDE;
@@ -200,13 +207,22 @@ logmel_kernel(const LogmelParams p, int tiles_per_utt, int total_tiles) {
                 if (t < p.T) {
                     float sv = 0.f;                                         // DataCollator pad value
                     if (t < Tb) { vmax = fmaxf(vmax, lg); sv = (lg + 4.0f) / 4.0f; }   // essentials.py:490
-                    p.out[((int64_t)b * p.M + m) * p.T + t] = sv;
+                    if (p.out_cl) s_cl[fr * clp + m] = __float2bfloat16_rn(sv);
+                    else p.out[((int64_t)b * p.M + m) * p.T + t] = sv;
                 }
             }
         }
         vmax = warp_max(vmax);
         if (lane == 0) s_red[warp] = vmax;
         __syncthreads();                                    // also: s_pow / s_pcm are free for the next tile
+        if (p.out_cl) {                                     // rows of CP bf16, two per 32-bit word: coalesced
+            const int wpr = p.CP >> 1;
+            uint32_t* dst = reinterpret_cast<uint32_t*>(p.out_cl + ((int64_t)b * p.T + t0) * p.CP);
+            for (int i = tid; i < FB * wpr; i += C::THREADS) {
+                const int fr = i / wpr, w = i - fr * wpr;
+                if (t0 + fr < p.T) dst[i] = *reinterpret_cast<const uint32_t*>(s_cl + fr * clp + 2 * w);
+            }
+        }
         if (warp == 0) {
             float v = lane < nwarp ? s_red[lane] : -INFINITY;
             v = warp_max(v);
@@ -232,6 +248,37 @@ __global__ void logmel_floor_kernel(float* out, const uint32_t* keys, const int3
             const float v = o[i];
             if (v < floor_s) o[i] = floor_s;
         }
+    }
+}
+
+// The same floor on the fused path's bf16 channels-last tensor, in place: rounding is monotone, so
+// max(bf16(x), bf16(floor)) == bf16(max(x, floor)) bit for bit.  One thread per (frame, 8 channels).
+__global__ void logmel_floor_cl_kernel(__nv_bfloat16* a, const uint32_t* keys, const int32_t* lengths,
+                                       int64_t n_samples, int hop, int M, int CP, int T) {
+    const int b = blockIdx.y;
+    const int64_t len = lengths ? (int64_t)lengths[b] : n_samples;
+    const int Tb = 1 + (int)(len / hop);
+    const __nv_bfloat16 fl = __float2bfloat16_rn(((key2f(keys[b]) - 8.0f) + 4.0f) / 4.0f);
+    const __nv_bfloat162 fl2 = __halves2bfloat162(fl, fl);
+    const int cpr = (M + 7) >> 3;                          // 16-byte chunks per row that hold real channels
+    const int64_t total = (int64_t)Tb * cpr;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int t = (int)(i / cpr), c8 = (int)(i - (int64_t)t * cpr);
+        uint4* ptr = reinterpret_cast<uint4*>(a + ((int64_t)b * T + t) * CP + c8 * 8);
+        uint4 q = *ptr;
+        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&q);
+        bool changed = false;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            __nv_bfloat162 v = __hmax2(h[j], fl2);
+            if (c8 * 8 + 2 * j + 1 >= M) {                 // tail chunk: padded channels stay 0
+                if (c8 * 8 + 2 * j >= M) v = h[j];
+                else v = __halves2bfloat162(__low2bfloat16(v), __high2bfloat16(h[j]));
+            }
+            changed |= (*reinterpret_cast<uint32_t*>(&v) != *reinterpret_cast<uint32_t*>(&h[j]));
+            h[j] = v;
+        }
+        if (changed) *ptr = q;
     }
 }
 
@@ -309,7 +356,8 @@ static int launch_logmel(const asrb_logmel_plan* pl, LogmelParams p, int64_t bat
     using C = LogmelCfg<NFFT, R, FB>;
     const int span = (FB - 1) * pl->hop + NFFT;
     size_t smem = sizeof(float) * (2 * ((span + 3) & ~3) + NFFT) + sizeof(float2) * (R * R + C::GROUPS * C::YSTRIDE) +
-                  sizeof(float) * (size_t)pl->n_mels * pl->kmax + sizeof(int) * 2 * pl->n_mels;
+                  sizeof(float) * (size_t)pl->n_mels * pl->kmax + sizeof(int) * (2 * pl->n_mels + 1) +
+                  (p.out_cl ? sizeof(__nv_bfloat16) * FB * (p.CP + 2) : 0);
     if (smem > 227 * 1024) return fail(ASRB_E_ARG, "asrb_logmel_f32: hop/n_mels need %zu B of shared memory", smem);
     auto kern = logmel_kernel<NFFT, R, FB>;
     ASRB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -328,8 +376,11 @@ static int launch_logmel(const asrb_logmel_plan* pl, LogmelParams p, int64_t bat
 
 // Shared by asrb_logmel_f32 and the fused pcm->hidden path: pass 1 only (values + keys).
 int logmel_pass1(const asrb_logmel_plan* pl, const float* pcm, int64_t batch, int64_t n_samples,
-                 int64_t stride, const int32_t* lengths, float* out, uint32_t* keys, cudaStream_t st) {
+                 int64_t stride, const int32_t* lengths, float* out, uint32_t* keys, cudaStream_t st,
+                 __nv_bfloat16* out_cl, int CP) {
     LogmelParams p;
+    p.out_cl = out_cl; p.CP = CP;
+    if (out_cl && (CP < pl->n_mels || (CP & 7))) return fail(ASRB_E_ARG, "log-mel: channels-last pitch %d for %d mels", CP, pl->n_mels);
     p.pcm = pcm; p.stride = stride; p.n_samples = n_samples; p.lengths = lengths;
     p.hop = pl->hop; p.T = (int)(1 + n_samples / pl->hop); p.M = pl->n_mels; p.kmax = pl->kmax;
     p.window = pl->d_window; p.twiddle = pl->d_twiddle; p.mel_lo = pl->d_lo; p.mel_cnt = pl->d_cnt;
@@ -340,6 +391,19 @@ int logmel_pass1(const asrb_logmel_plan* pl, const float* pcm, int64_t batch, in
                  4.0 * batch * ((double)n_samples + (double)pl->n_mels * p.T));
     if (pl->n_fft == 400) return launch_logmel<400, 20, 32>(pl, p, batch, st);
     return launch_logmel<1024, 32, 16>(pl, p, batch, st);
+}
+
+// Floor of the fused path (after logmel_pass1 with out_cl).
+int logmel_floor_cl(const asrb_logmel_plan* pl, __nv_bfloat16* a, int CP, const uint32_t* keys, const int32_t* lengths,
+                    int64_t batch, int64_t n_samples, cudaStream_t st) {
+    const int T = (int)(1 + n_samples / pl->hop);
+    const int64_t per = (int64_t)T * ((pl->n_mels + 7) / 8);
+    int gx = (int)((per + 256 * 4 - 1) / (256 * 4));
+    if (gx < 1) gx = 1;
+    ProfScope ps("logmel_floor", st, 0.0, 4.0 * batch * T * pl->n_mels);
+    logmel_floor_cl_kernel<<<dim3(gx, (unsigned)batch), 256, 0, st>>>(a, keys, lengths, n_samples, pl->hop, pl->n_mels, CP, T);
+    ASRB_LAUNCH_CHECK();
+    return ASRB_OK;
 }
 
 }  // namespace asrb
