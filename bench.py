@@ -11,9 +11,10 @@ same through the public API from pinned HOST buffers (H2D of the PCM and D2H of 
 per-utterance pooled hidden state inside the timed region).  `roofline`: the dominant kernel
 (tcgen05 conv-GEMM + LayerNorm) from per-launch CUDA events.  `cpu_baseline`: the oracle
 (port of the reference) on this box's host cores on a bounded sample.
-Under torchrun (N > 1) each rank runs its own 64-clip shard (weak scaling) and the encoder
-outputs are exchanged over NCCL (grouped send/recv straight into the gathered tensor); the
-exchange of step i overlaps the compute of step i+1 and all of it is inside the timed region.
+Under torchrun (N > 1) each rank runs its own 64-clip shard (weak scaling) and pushes its encoder
+outputs into every peer's gathered tensor over NVLink (symmetric memory + copy engines; NCCL
+send/recv if that is unavailable); the exchange of step i overlaps the compute of step i+1 and
+all of it is inside the timed region.
 """
 import argparse
 import json
@@ -130,7 +131,7 @@ def workload_config(args, world):
     return {"workload": f"log-mel (16 kHz, n_fft {N_FFT}, hop {HOP}, {MELS} mel) + AudioEncoder(D={DIMS}, H={HEAD}, L={LAYER}, "
                         f"enc={bool(args.enc)}) forward, {PER_GPU_BATCH} x {SECS} s clips per GPU",
             "global_batch": PER_GPU_BATCH * world, "clip_seconds": SECS, "frames_per_clip": 1 + SECS * SR // HOP,
-            "parallelism": f"utterance-sharded x{world}" + (", NCCL all-gather of encoder outputs" if world > 1 else ""),
+            "parallelism": f"utterance-sharded x{world}" + (", encoder outputs gathered on every rank over NVLink" if world > 1 else ""),
             "l2": "inputs larger than L2 (123 MB PCM + 197 MB activations per tensor per step)",
             "weights": "random init", "enc": bool(args.enc)}
 
