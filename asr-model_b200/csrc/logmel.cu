@@ -198,12 +198,23 @@ logmel_kernel(const LogmelParams p, int tiles_per_utt, int total_tiles) {
             const int t = t0 + fr;
             const float* pw = s_pow + fr * C::NB;
             for (int m = warp * MSUB + lane / FW; m < p.M; m += nwarp * MSUB) {
-                const int lo = s_lo[m], cnt = s_cnt[m];
-                const float* w = s_melw + m * p.kmax;
+                // banded filter, taps zero-padded to a multiple of 4: one broadcast 16-byte weight load per 4 taps
+                const int lo = s_lo[m], n4 = (s_cnt[m] + 3) >> 2;
+                const float4* w4 = reinterpret_cast<const float4*>(s_melw + m * p.kmax);
+                const float* px = pw + lo;
                 float acc = 0.f;
-                for (int i = 0; i < cnt; ++i) acc = fmaf(w[i], pw[lo + i], acc);
+#pragma unroll 1                                               // 1-3 trips: remainder code of an unrolled loop costs more than it saves
+                for (int q = 0; q < n4; ++q) {
+                    const float4 w = w4[q];
+                    acc = fmaf(w.x, px[4 * q], acc);
+                    acc = fmaf(w.y, px[4 * q + 1], acc);
+                    acc = fmaf(w.z, px[4 * q + 2], acc);
+                    acc = fmaf(w.w, px[4 * q + 3], acc);
+                }
                 // log10 through MUFU lg2 (abs error ~2^-22 in log2: 7e-8 in log10)   essentials.py:488
-                const float lg = __log2f(fmaxf(acc, 1e-10f)) * 0.30102999566398120f;
+                float lg;                                                   // argument >= 1e-10: never denormal, plain MUFU.LG2
+                asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(fmaxf(acc, 1e-10f)));
+                lg *= 0.30102999566398120f;
                 if (t < p.T) {
                     float sv = 0.f;                                         // DataCollator pad value
                     if (t < Tb) { vmax = fmaxf(vmax, lg); sv = (lg + 4.0f) / 4.0f; }   // essentials.py:490
@@ -306,6 +317,7 @@ extern "C" int asrb_logmel_plan_create(int n_fft, int hop, int n_mels, const flo
             if (fbank_host[(size_t)f * n_mels + m] != 0.0f) { if (first < 0) first = f; last = f; }
         if (first >= 0) { lo[m] = first; cnt[m] = last - first + 1; if (cnt[m] > kmax) kmax = cnt[m]; }
     }
+    kmax = (kmax + 3) & ~3;                                // taps padded with zeros to a multiple of 4 (16-byte weight loads)
     std::vector<float> w((size_t)n_mels * kmax, 0.f);
     for (int m = 0; m < n_mels; ++m)
         for (int i = 0; i < cnt[m]; ++i) w[(size_t)m * kmax + i] = fbank_host[(size_t)(lo[m] + i) * n_mels + m];
