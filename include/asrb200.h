@@ -179,7 +179,8 @@ int asrb_profile_get(int index, const char** tag, float* ms, double* flops, doub
  *             down the frames -> dw_act |
  *           5 bias+res+act -> depthwise(dw_w [kw][N], dw_b) -> dw_act (+ pos [T][N]).
  * act / dw_act: 0 none | 1 GELU | 2 ReLU | 3 SiLU | 4 GELU(GELU).  K % 64 == 0, N % 128 == 0
- * (N % 256 == 0 for 1, 4, 5); kw in {3, 15}. */
+ * (N % 256 == 0 for 4).  The fused depthwise epilogues are built for the combinations the encoder uses:
+ * 4 with kw = 15, dw_act = SiLU; 5 with kw = 3, act = GELU, dw_act in {GELU, GELU(GELU)}. */
 int asrb_test_gemm_tc(const void* a, const void* w, const float* bias, const void* res,
                       const float* gamma, const float* beta, void* out,
                       int64_t B, int64_t T, int K, int N, int taps, int epilogue, int act,

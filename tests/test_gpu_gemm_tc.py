@@ -71,6 +71,19 @@ CASES = [
     (2, 300, 256, 256, 1, 5, 1),        # residual + GELU -> depthwise-3 -> GELU(GELU)
     (2, 127, 512, 512, 1, 5, 1),
     (5, 1001, 512, 512, 1, 5, 1),
+    # channel-major kernels (gemm_tct.cu): tile edges (254 frames per residual tile, 112 per GLU tile), tiny T,
+    # one channel tile, the generic and the 1024-wide store paths
+    (1, 1, 64, 128, 1, 5, 1),
+    (2, 2, 128, 128, 1, 5, 1),
+    (1, 254, 64, 128, 1, 5, 1),
+    (1, 255, 64, 128, 1, 5, 1),
+    (3, 257, 128, 256, 1, 5, 1),
+    (1, 600, 256, 1024, 1, 5, 1),
+    (1, 1, 64, 256, 1, 4, 0),
+    (2, 112, 64, 256, 1, 4, 0),
+    (2, 113, 128, 256, 1, 4, 0),
+    (1, 225, 64, 256, 1, 4, 0),
+    (1, 500, 256, 2048, 1, 4, 0),
 ]
 
 
