@@ -108,13 +108,17 @@ def test_gemm_tc_matches_torch(built_lib, B, T, K, N, taps, epi, act):
         pos = torch.randn(T, n_out, device="cuda", generator=g) if (epi == 5 and T % 2 == 0) else None
         dw = (dw_w, dw_b, kw, act2, pos)
         dw_args = (dw_w.data_ptr(), dw_b.data_ptr(), kw, act2, pos.data_ptr() if pos is not None else None)
-    out = torch.full((B, T, n_out), float("nan"), device="cuda", dtype=torch.bfloat16)
+    guard = 64 * n_out                                  # sentinel rows before and after: nothing may be written outside the tensor
+    buf = torch.full((B * T * n_out + 2 * guard,), 12345.0, device="cuda", dtype=torch.bfloat16)
+    out = buf[guard: guard + B * T * n_out].view(B, T, n_out)
+    out.fill_(float("nan"))
     rc = lib.asrb_test_gemm_tc(a.data_ptr(), w.data_ptr(), bias.data_ptr(), res.data_ptr() if res is not None else None,
                                gamma.data_ptr(), beta.data_ptr(), out.data_ptr(), B, T, K, N, taps, epi, act, *dw_args, None)
     built_lib.check(rc, "asrb_test_gemm_tc")
     torch.cuda.synchronize()
     ref = _ref(a, w, bias, res, gamma, beta, taps, epi, act, N, dw)
     assert not torch.isnan(out.float()).any(), "rows were left unwritten"
+    assert bool((buf[:guard] == 12345.0).all()) and bool((buf[-guard:] == 12345.0).all()), "wrote outside the output tensor"
     err = (out.float() - ref).abs()
     tol = 2e-2 + 1e-2 * ref.abs()                      # bf16 store rounding dominates
     assert bool((err <= tol).all()), f"max err {float(err.max())} at {int(err.argmax())}"
