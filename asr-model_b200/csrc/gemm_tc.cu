@@ -21,7 +21,7 @@ namespace asrb {
 template <int BN, int EPI>
 __global__ void __launch_bounds__(TcCfg<BN>::THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
-               const __grid_constant__ CUtensorMap map_out, const TcParams p) {
+               const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_ah, const TcParams p) {
     using C = TcCfg<BN>;
     constexpr int STAGES = C::STAGES, NG = C::NG;
     extern __shared__ __align__(1024) unsigned char smem[];                  // SWIZZLE_128B tiles need 1024-B alignment
@@ -54,9 +54,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_out) : "memory");
+        if (is_ln) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_ah) : "memory");
     }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        // pair (cl = 2): both CTAs read the same frame tile, so each loads half of it and multicasts it to both; a
+        // slot is free once BOTH CTAs' MMAs have consumed it (two arrivals on empty)
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), (uint32_t)cl); }
         for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), NG * 128); mbar_init(xbar(a), BM); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -87,7 +90,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         mbar_expect_tx(full_bar(s), C::STAGE_BYTES);
                         const int tap = kb / kb_per_tap, kc = kb - tap * kb_per_tap;
                         const uint32_t sa = smem_u32(smem + s * C::STAGE_BYTES);
-                        tma_load_3d(sa, &map_a, kc * BK, t0 + tap - pad, b, full_bar(s));
+                        if (is_ln && cl > 1)       // my half of the shared frame tile (64 rows = 8 KB), delivered to both CTAs
+                            tma_load_3d_mc(sa + crank * (C::A_BYTES / 2), &map_ah, kc * BK, t0 + tap - pad + (int)crank * (BM / 2), b, full_bar(s), (uint16_t)3);
+                        else
+                            tma_load_3d(sa, &map_a, kc * BK, t0 + tap - pad, b, full_bar(s));
                         tma_load_2d(sa + C::A_BYTES, &map_w, kb * BK, n0, full_bar(s));
                     }
                     __syncwarp();
@@ -117,7 +123,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
                         for (int kk = 0; kk < BK / 16; ++kk)
                             tc_mma(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, (uint32_t)((kb | kk) != 0));
-                        tc_commit(empty_bar(s));                              // frees the smem slot when the MMAs retire
+                        if (is_ln && cl > 1) tc_commit_mc(empty_bar(s), (uint16_t)3);   // the peer writes half of my slot: tell both
+                        else tc_commit(empty_bar(s));                         // frees the smem slot when the MMAs retire
                     }
                     __syncwarp();
                     if (++s == STAGES) { s = 0; ph ^= 1; }
@@ -304,8 +311,8 @@ bool tc_gemm_supported(int K, int N, int epi) {
 }
 
 template <int BN, int EPI>
-static int launch_one(const CUtensorMap& ma, const CUtensorMap& mw, const CUtensorMap& mo, const TcParams& p, int units,
-                      cudaStream_t st) {
+static int launch_one(const CUtensorMap& ma, const CUtensorMap& mw, const CUtensorMap& mo, const CUtensorMap& mah,
+                      const TcParams& p, int units, cudaStream_t st) {
     auto kern = gemm_tc_kernel<BN, EPI>;
     ASRB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::SMEM));
     const int cl = p.cluster;
@@ -318,7 +325,7 @@ static int launch_one(const CUtensorMap& ma, const CUtensorMap& mw, const CUtens
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = (unsigned)cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    ASRB_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mw, mo, p));
+    ASRB_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mw, mo, mah, p));
     ASRB_LAUNCH_CHECK();
     return ASRB_OK;
 }
@@ -368,7 +375,9 @@ int launch_gemm_tc(const TcGemmArgs& a, cudaStream_t st) {
     const int units = a.epilogue == TC_LN ? p.m_tiles : p.m_tiles * p.n_chunks;
     ProfScope ps(tags[a.epilogue], st, 2.0 * a.B * a.T * (double)a.N * a.K * a.taps,
                  2.0 * a.B * a.T * ((double)a.K + n_out * (a.out_f32 ? 2 : 1) + (a.res ? n_out : 0)) + 2.0 * a.N * a.K * a.taps);
-#define ASRB_TC(BN_, EPI_) return launch_one<BN_, EPI_>(ma, mw, mo, p, units, st)
+    CUtensorMap mah = ma;                                                    // 64-row boxes of the same tensor (pair multicast)
+    if (p.cluster > 1) ASRB_TRY(make_act_map(&mah, a.A, a.B, a.T, a.K, BM / 2));
+#define ASRB_TC(BN_, EPI_) return launch_one<BN_, EPI_>(ma, mw, mo, mah, p, units, st)
     if (bn == 256) {
         switch (a.epilogue) {
             case TC_BIAS_ACT: ASRB_TC(256, TC_BIAS_ACT);
