@@ -212,7 +212,8 @@ gemm_tct_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 16 * 32); }
+        // the residual kernel's 16 epilogue warps share a unit; the GLU kernel's two teams of 8 own one accumulator stage each
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), RES ? 16 * 32 : 8 * 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -351,36 +352,42 @@ gemm_tct_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
                         dw3_chunk<true, NO, ACT2>(v, pa, pb, hb0, kk, p, tS, t_lo, t_hi, false, false, row0, c);
                 }
             } else {
-                // ---- GLU -> depthwise-15 -> act2.  Group g emits tile columns [8 + 28g, 36 + 28g) from the
-                // 44-column window starting at column 28g (window index i <-> frame tw + i) ----
-                const int ws = 28 * g, tw = tb + ws;
-                float h[44];
+                // ---- GLU -> depthwise-15 -> act2.  Two TEAMS of 8 warps alternate over the units (team = accumulator
+                // stage), so while one team waits on TMEM loads at the head of its unit the other is in the FFMA-heavy
+                // part of the previous one.  A warp emits two 28-frame groups of its unit one after the other: group gg
+                // covers tile columns [8 + 28 gg, 36 + 28 gg) from the 44-column window starting at column 28 gg
+                // (window index i <-> frame tw + i) ----
+                if ((it & 1) != (g >> 1)) continue;         // the other team's unit
                 mbar_wait_sleep(tfull_bar(a), aph, 32);
                 tc_fence_after();
-                {   // GLU: (v + bv) * sigmoid(g + bg) = hv + hv tanh((g + bg) / 2),  hv = (v + bv) / 2
-                    float gt[32];
-                    tmem_ld32_nw(acc + ws, h);
-                    tmem_ld32_nw(acc + 128 + ws, gt);
-                    tmem_ld_wait();
+#pragma unroll 1
+                for (int pass = 0; pass < 2; ++pass) {
+                    const int ws = 28 * ((g & 1) * 2 + pass), tw = tb + ws;
+                    float h[44];
+                    {   // GLU: (v + bv) * sigmoid(g + bg) = hv + hv tanh((g + bg) / 2),  hv = (v + bv) / 2
+                        float gt[32];
+                        tmem_ld32_nw(acc + ws, h);
+                        tmem_ld32_nw(acc + 128 + ws, gt);
+                        tmem_ld_wait();
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) { const float hv = fmaf(h[i], 0.5f, hb0); h[i] = fmaf(hv, tanh_approx(fmaf(gt[i], 0.5f, hb1)), hv); }
-                }
-                {
-                    float gt[12];
-                    tmem_ld8_nw(acc + ws + 32, h + 32);
-                    tmem_ld4_nw(acc + ws + 40, h + 40);
-                    tmem_ld8_nw(acc + 128 + ws + 32, gt);
-                    tmem_ld4_nw(acc + 128 + ws + 40, gt + 8);
-                    tmem_ld_wait();
-                    tc_fence_before();
-                    mbar_arrive(tempty_bar(a));             // accumulators drained
+                        for (int i = 0; i < 32; ++i) { const float hv = fmaf(h[i], 0.5f, hb0); h[i] = fmaf(hv, tanh_approx(fmaf(gt[i], 0.5f, hb1)), hv); }
+                    }
+                    {
+                        float gt[12];
+                        tmem_ld8_nw(acc + ws + 32, h + 32);
+                        tmem_ld4_nw(acc + ws + 40, h + 40);
+                        tmem_ld8_nw(acc + 128 + ws + 32, gt);
+                        tmem_ld4_nw(acc + 128 + ws + 40, gt + 8);
+                        tmem_ld_wait();
+                        if (pass == 1) { tc_fence_before(); mbar_arrive(tempty_bar(a)); }   // this warp's last TMEM read of the unit
 #pragma unroll
-                    for (int i = 0; i < 12; ++i) { const float hv = fmaf(h[32 + i], 0.5f, hb0); h[32 + i] = fmaf(hv, tanh_approx(fmaf(gt[i], 0.5f, hb1)), hv); }
+                        for (int i = 0; i < 12; ++i) { const float hv = fmaf(h[32 + i], 0.5f, hb0); h[32 + i] = fmaf(hv, tanh_approx(fmaf(gt[i], 0.5f, hb1)), hv); }
+                    }
+                    const int t0 = tw + 8;                  // frame of output 0 (>= 0)
+                    __nv_bfloat16* op = p.out + (row0 + t0) * ld + c;
+                    if (tw >= 0 && tw + 43 < p.T) dw15_emit<false, NO, ACT2>(h, k, op, ld, tw, p.T);
+                    else dw15_emit<true, NO, ACT2>(h, k, op, ld, tw, p.T);
                 }
-                const int t0 = tw + 8;                      // frame of output 0 (>= 0)
-                __nv_bfloat16* op = p.out + (row0 + t0) * ld + c;
-                if (tw >= 0 && tw + 43 < p.T) dw15_emit<false, NO, ACT2>(h, k, op, ld, tw, p.T);
-                else dw15_emit<true, NO, ACT2>(h, k, op, ld, tw, p.T);
             }
         }
     }
