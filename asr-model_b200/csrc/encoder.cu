@@ -280,27 +280,41 @@ int tc_gemm_ln(const __nv_bfloat16* A, const __nv_bfloat16* W, const float* bias
     return launch_layernorm(tmp, nullptr, gamma, beta, out, DT_BF16, B * T, N, 1e-5f, st);
 }
 
-// Everything after the stem input is in place (a0 for in_ch == mels, x itself for in_ch == 1).
-int encoder_body(asrb_encoder* e, const EncBuffers& w, const float* x_c1, int in_ch, int64_t B, int64_t T,
-                 void* out, int out_dtype, cudaStream_t st) {
-    const int D = e->cfg.dims, L = e->cfg.layer;
+// Stem of one feature stream: conv1 (mels -> D, k3; its input is already in w.a0) or conv2 (1 -> D, k3, straight
+// from x), model.py:152-155, + layer 0's leading activation, written to X (B x T rows).
+int encoder_stem(asrb_encoder* e, const EncBuffers& w, const float* x_c1, int in_ch, int64_t B, int64_t T, void* X, cudaStream_t st) {
+    const int D = e->cfg.dims;
     const bool bf = e->cfg.compute == ASRB_BF16;
     const DType dt = bf ? DT_BF16 : DT_F32;
     const Act stem_act = ACT_GELU;                        // layer 0's leading act_fn (model.py:143)
-    const int64_t rows = B * T;
-
-    // ---- stem: conv1 (mels -> D, k3) or conv2 (1 -> D, k3), model.py:152-155 ----
     if (in_ch == 1) {
         if (!e->stem2_f) return fail(ASRB_E_WEIGHTS, "conv2.0.weight was not supplied: single-channel input unsupported");
-        ASRB_TRY(launch_gemm_simt(x_c1, DT_F32, e->stem2_f, e->stem2_b, nullptr, w.X, dt, B, T, 1, D, 3, stem_act, st));
-    } else if (bf) {
-        TcGemmArgs g{};
-        g.A = (const __nv_bfloat16*)w.a0; g.W = e->stem1_h; g.bias = e->stem1_b; g.out = w.X;
-        g.B = B; g.T = T; g.K = e->CP; g.N = D; g.taps = 3; g.epilogue = TC_BIAS_ACT; g.act = stem_act;
-        ASRB_TRY(launch_gemm_tc(g, st));
-    } else {
-        ASRB_TRY(launch_gemm_simt(w.a0, DT_F32, e->stem1_f, e->stem1_b, nullptr, w.X, DT_F32, B, T, e->cfg.mels, D, 3, stem_act, st));
+        return launch_gemm_simt(x_c1, DT_F32, e->stem2_f, e->stem2_b, nullptr, X, dt, B, T, 1, D, 3, stem_act, st);
     }
+    if (bf) {
+        TcGemmArgs g{};
+        g.A = (const __nv_bfloat16*)w.a0; g.W = e->stem1_h; g.bias = e->stem1_b; g.out = X;
+        g.B = B; g.T = T; g.K = e->CP; g.N = D; g.taps = 3; g.epilogue = TC_BIAS_ACT; g.act = stem_act;
+        return launch_gemm_tc(g, st);
+    }
+    return launch_gemm_simt(w.a0, DT_F32, e->stem1_f, e->stem1_b, nullptr, X, DT_F32, B, T, e->cfg.mels, D, 3, stem_act, st);
+}
+
+int encoder_layers(asrb_encoder* e, const EncBuffers& w, int64_t B, int64_t T, void* out, int out_dtype, cudaStream_t st);
+
+// Everything after the stem input is in place (a0 for in_ch == mels, x itself for in_ch == 1).
+int encoder_body(asrb_encoder* e, const EncBuffers& w, const float* x_c1, int in_ch, int64_t B, int64_t T,
+                 void* out, int out_dtype, cudaStream_t st) {
+    ASRB_TRY(encoder_stem(e, w, x_c1, in_ch, B, T, w.X, st));
+    return encoder_layers(e, w, B, T, out, out_dtype, st);
+}
+
+// The layer stack (and the optional TransformerEncoderLayer) over B x T rows whose stem output sits in w.X.
+int encoder_layers(asrb_encoder* e, const EncBuffers& w, int64_t B, int64_t T, void* out, int out_dtype, cudaStream_t st) {
+    const int D = e->cfg.dims, L = e->cfg.layer;
+    const bool bf = e->cfg.compute == ASRB_BF16;
+    const DType dt = bf ? DT_BF16 : DT_F32;
+    const int64_t rows = B * T;
 
     ASRB_TRY(launch_pos_table(w.pos, e->pos_scales, T, D, st));
 
@@ -424,6 +438,33 @@ extern "C" int asrb_encoder_forward(asrb_encoder* e, const float* x, int64_t B, 
         ASRB_TRY(launch_to_channels_last(x, w.a0, bf ? DT_BF16 : DT_F32, B, in_ch, bf ? e->CP : in_ch, T,
                                          nullptr, nullptr, 0, 1, false, st));
     return encoder_body(e, w, x, in_ch, B, T, out, out_dtype, st);
+}
+
+extern "C" int asrb_encoder_forward_streams(asrb_encoder* e, int32_t n_streams, const float* const* x, const int32_t* in_ch,
+                                            int64_t B, int64_t T, void* out, int out_dtype, void* ws, size_t ws_bytes,
+                                            void* stream) {
+    if (n_streams < 1 || n_streams > 8 || !x || !in_ch) return fail(ASRB_E_ARG, "asrb_encoder_forward_streams: bad stream list");
+    for (int s = 0; s < n_streams; ++s) {
+        ASRB_TRY(check_forward_args(e, B * n_streams, in_ch[s], T, out, out_dtype));
+        if (B * T > 0 && !x[s]) return fail(ASRB_E_ARG, "asrb_encoder_forward_streams: NULL input %d", s);
+    }
+    if (B == 0 || T == 0) return ASRB_OK;
+    const int64_t Bt = B * n_streams;
+    if (!ws || ws_bytes < enc_ws_bytes(e, Bt, T) || ((uintptr_t)ws & 255))
+        return fail(ASRB_E_WORKSPACE, "asrb_encoder_forward_streams: workspace NULL, not 256-B aligned or smaller than %zu B", enc_ws_bytes(e, Bt, T));
+    ASRB_TRY(require_sm100());
+    cudaStream_t st = (cudaStream_t)stream;
+    EncBuffers w = carve(e, Bt, T, ws, ws_bytes);
+    if (!w.ok) return fail(ASRB_E_WORKSPACE, "asrb_encoder_forward_streams: workspace carve failed");
+    const bool bf = e->cfg.compute == ASRB_BF16;
+    const size_t es = bf ? 2 : 4;
+    for (int s = 0; s < n_streams; ++s) {                  // stems one by one (conv1 | conv2), into stream s's rows of X
+        if (in_ch[s] != 1)
+            ASRB_TRY(launch_to_channels_last(x[s], w.a0, bf ? DT_BF16 : DT_F32, B, in_ch[s], bf ? e->CP : in_ch[s], T,
+                                             nullptr, nullptr, 0, 1, false, st));
+        ASRB_TRY(encoder_stem(e, w, x[s], in_ch[s], B, T, (char*)w.X + (size_t)s * B * T * e->cfg.dims * es, st));
+    }
+    return encoder_layers(e, w, Bt, T, out, out_dtype, st);   // one pass of the layer stack over all streams
 }
 
 extern "C" size_t asrb_pcm_to_hidden_workspace_bytes(const asrb_logmel_plan* pl, const asrb_encoder* e, int64_t B,

@@ -150,11 +150,34 @@ class AudioEncoder(nn.Module):
                 ws.data_ptr(), ws.numel(), _lib.stream_ptr()), "asrb_encoder_forward")
         return out
 
+    def _process_streams(self, feats):
+        """Several same-shaped feature streams (the reference's TensorDict {a, b, c}) through one pass of the layer
+        stack: ``{name: [B, C_s, T]}`` -> ``{name: [B, T, dims]}`` (views of one tensor)."""
+        names = list(feats)
+        xs = [feats[k].unsqueeze(0) if feats[k].dim() == 2 else feats[k] for k in names]
+        xs = [x.float().contiguous() for x in xs]
+        B, _, T = xs[0].shape
+        same = all(x.is_cuda and x.shape[0] == B and x.shape[2] == T and x.device == xs[0].device for x in xs)
+        if self.training or not same or len(xs) < 2 or len(xs) > 8:
+            return {k: self._process_feature(feats[k]) for k in names}
+        dev = xs[0].device
+        h = self._handle(dev)
+        n = len(xs)
+        out = torch.empty(n * B, T, self.dims, device=dev, dtype=self.out_dtype)
+        ws = self._workspace(dev, self._lib.asrb_encoder_workspace_bytes(h, n * B, T))
+        ptrs = (C.c_void_p * n)(*[x.data_ptr() for x in xs])
+        chans = (C.c_int32 * n)(*[x.shape[1] for x in xs])
+        with torch.cuda.device(dev):
+            _lib.check(self._lib.asrb_encoder_forward_streams(
+                h, n, ptrs, chans, B, T, out.data_ptr(), _lib.BF16 if self.out_dtype == torch.bfloat16 else _lib.F32,
+                ws.data_ptr(), ws.numel(), _lib.stream_ptr()), "asrb_encoder_forward_streams")
+        return {k: out[i * B:(i + 1) * B] for i, k in enumerate(names)}
+
     def forward(self, x):
         if hasattr(x, "apply") and not torch.is_tensor(x):          # TensorDict (model.py:166-167)
             return x.apply(self._process_feature)
-        if isinstance(x, dict):
-            return {k: self._process_feature(v) for k, v in x.items() if v is not None}
+        if isinstance(x, dict):                                     # same streams as a plain dict: batched
+            return self._process_streams({k: v for k, v in x.items() if v is not None})
         return self._process_feature(x)
 
     def forward_pcm(self, wave: torch.Tensor, frontend, lengths: Optional[torch.Tensor] = None,

@@ -126,6 +126,15 @@ int asrb_encoder_forward(asrb_encoder* enc, const float* x, int64_t batch, int32
                          int64_t frames, void* out, int out_dtype,
                          void* workspace, size_t workspace_bytes, void* stream);
 
+/* Several feature streams of the same shape through ONE pass of the layer stack (Model.forward / generate encode
+ * the TensorDict {a, b, c} = spectrogram / waveform / pitch with the same encoder, model.py:165-167, 657-665): stream s
+ * is x[s] [batch][in_ch[s]][frames] (in_ch = mels -> conv1, 1 -> conv2); out is [n_streams * batch][frames][dims], stream s
+ * at rows [s * batch, (s + 1) * batch).  Results equal n_streams calls of asrb_encoder_forward; the workspace is that of
+ * asrb_encoder_workspace_bytes(enc, n_streams * batch, frames).  n_streams <= 8. */
+int asrb_encoder_forward_streams(asrb_encoder* enc, int32_t n_streams, const float* const* x, const int32_t* in_ch,
+                                 int64_t batch, int64_t frames, void* out, int out_dtype,
+                                 void* workspace, size_t workspace_bytes, void* stream);
+
 /* Fused hot path: PCM -> log-mel -> encoder without materialising the fp32 [B,M,T]
  * feature tensor unless `logmel_out` is non-NULL.  Equivalent to
  * asrb_logmel_f32 followed by asrb_encoder_forward. */

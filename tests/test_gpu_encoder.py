@@ -133,6 +133,25 @@ def test_dict_input_and_2d_input(ab):
     assert set(d) == {"a", "b"} and torch.equal(d["a"], y)
 
 
+@pytest.mark.parametrize("compute", ["fp32", "bf16"])
+def test_three_streams_in_one_pass_equal_three_calls(ab, compute):
+    """{a, b, c} = spectrogram / waveform / pitch streams through one pass of the layer stack
+    (asrb_encoder_forward_streams) must equal three separate forwards, bit for bit."""
+    sd = oracle.random_encoder_state_dict(80, 256, 2, True, seed=11, perturb=True)
+    m = _enc(ab, sd, 80, 256, 4, 2, True, compute)
+    g = torch.Generator().manual_seed(3)
+    feats = {"a": torch.randn(3, 80, 300, generator=g).cuda(), "b": torch.randn(3, 1, 300, generator=g).cuda(),
+             "c": torch.randn(3, 1, 300, generator=g).cuda()}
+    sep = {k: m(v).clone() for k, v in feats.items()}
+    both = m(feats)
+    assert set(both) == {"a", "b", "c"}
+    for k in feats:
+        assert both[k].shape == (3, 300, 256) and torch.equal(both[k], sep[k]), k
+    ref = oracle.audio_encoder_forward(sd, feats["b"].cpu(), 4)
+    if compute == "fp32":
+        assert float((both["b"].float().cpu() - ref).abs().max()) <= 1e-4
+
+
 def test_weight_update_invalidates_the_packed_copy(ab):
     sd = oracle.random_encoder_state_dict(80, 128, 1, False, seed=8, perturb=True)
     m = _enc(ab, sd, 80, 128, 4, 1, False, "fp32")
