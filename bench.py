@@ -282,10 +282,10 @@ def main():
         traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["bytes_per_launch"]
     except Exception:
         pass
-    # The dominant kernel is the tcgen05 implicit-GEMM `gemm_tc_kernel<BN, EPI>`: one kernel template whose
-    # epilogue variants (stem, k3+LayerNorm, 1x1+GLU+depthwise-15, 1x1+residual+depthwise-3, ...) make up
-    # > 90 % of the step.  The roofline entry aggregates its launches (per launch = totals / launches);
-    # the per-variant numbers are in "kernels".
+    # The dominant kernels are the tcgen05 implicit GEMMs: `gemm_tc_kernel<BN, EPI>` (lanes = frames: stem,
+    # k3+LayerNorm) and `gemm_tct_kernel<EPI, NO, ACT2>` (lanes = channels: 1x1+GLU+depthwise-15,
+    # 1x1+residual+depthwise-3), > 90 % of the step, three of them within 2x of each other.  The roofline entry
+    # aggregates their launches (per launch = totals / launches); the per-kernel numbers are in "kernels".
     fam = {t: d for t, d in by.items() if t.startswith("gemm_tc")}
     other = max((t for t in by if t not in fam), key=lambda t: by[t]["ms"], default=None)
     fam_ms = sum(d["ms"] for d in fam.values())
@@ -295,7 +295,7 @@ def main():
         tr = sum(traffic[t] * (d["n"]) for t, d in fam.items() if t in traffic)
         tr_n = sum(d["n"] for t, d in fam.items() if t in traffic)
         achieved = fl / fam_ms / 1e9                       # TFLOP/s
-        roof = {"kernel": "gemm_tc_kernel<BN,EPI> (%d launches per step: %s)" % (n // psteps, ", ".join(sorted(fam))),
+        roof = {"kernel": "tcgen05 GEMMs gemm_tc_kernel<BN,EPI> + gemm_tct_kernel<EPI,NO,ACT2> (%d launches per step: %s)" % (n // psteps, ", ".join(sorted(fam))),
                 "bound": "tensor", "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
                 "frac": achieved / pk["tf_sustained"],
                 "traffic": tr / tr_n if tr_n else None, "traffic_unit": "DRAM bytes per launch (ncu, profiles/traffic.json)",
