@@ -154,7 +154,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const uint32_t aph = (uint32_t)(it / acc_stages) & 1u;
             const bool row_ok = t0 + r >= 0 && t0 + r < p.T;
             const int64_t grow = (int64_t)b * p.T + t0 + r;
-            mbar_wait_sleep(tfull_bar(a), aph, 32);        // 16 warps wait here: sleeping between probes leaves the issue slots (and power) to the MMA side
+            mbar_wait_backoff(tfull_bar(a), aph, 32, 512);  // 16 warps wait here for most of a tile time: back off, leave issue slots and power to the MMA side
             tc_fence_after();
             const uint32_t acc = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(a * nbu * BN);
 

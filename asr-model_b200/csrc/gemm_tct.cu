@@ -326,7 +326,7 @@ gemm_tct_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
                 // group g emits tile columns [64g - 1, 64g + 63) ∩ [1, 255): frames [t_lo, t_hi)
                 const int S0 = 64 * g;
                 const int t_lo = tb + max(S0 - 1, 1), t_hi = min(tb + S0 + 63, p.T);
-                mbar_wait_sleep(tfull_bar(a), aph, 32);
+                mbar_wait_backoff(tfull_bar(a), aph, 32, 256);
                 tc_fence_after();
                 float pa = 0.f, pb = 0.f;
 #pragma unroll 1
@@ -358,7 +358,7 @@ gemm_tct_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
                 // covers tile columns [8 + 28 gg, 36 + 28 gg) from the 44-column window starting at column 28 gg
                 // (window index i <-> frame tw + i) ----
                 if ((it & 1) != (g >> 1)) continue;         // the other team's unit
-                mbar_wait_sleep(tfull_bar(a), aph, 32);
+                mbar_wait_backoff(tfull_bar(a), aph, 32, 256);
                 tc_fence_after();
 #pragma unroll 1
                 for (int pass = 0; pass < 2; ++pass) {

@@ -47,6 +47,21 @@ __device__ __forceinline__ bool elect_one() {          // true in exactly one la
     asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
     return pred != 0;
 }
+// the same with the sleep doubling up to ns_max: for the epilogue warps, which wait for most of a tile time on the
+// accumulator (polling at 32 ns was ~40 % of the k3+LayerNorm kernel's executed instructions)
+__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity, uint32_t ns, uint32_t ns_max) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .u32 t;\n\t"
+        "mov.u32 t, %2;\n\t"
+        "WAITB_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAITB_DONE;\n\t"
+        "nanosleep.u32 t;\n\t"
+        "shl.b32 t, t, 1;\n\t"
+        "min.u32 t, t, %3;\n\t"
+        "bra WAITB_LOOP;\n\t"
+        "WAITB_DONE:\n\t}" ::"r"(bar), "r"(parity), "r"(ns), "r"(ns_max) : "memory");
+}
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
                  ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
