@@ -152,6 +152,22 @@ def test_three_streams_in_one_pass_equal_three_calls(ab, compute):
         assert float((both["b"].float().cpu() - ref).abs().max()) <= 1e-4
 
 
+@pytest.mark.parametrize("mels,D,H,L,enc,B,T", [
+    (80, 128, 4, 1, False, 2, 37), (80, 384, 4, 1, False, 2, 513), (128, 640, 5, 1, False, 1, 700),
+    (80, 768, 6, 1, True, 2, 260), (80, 1024, 16, 1, False, 1, 400)])
+def test_bf16_other_widths_and_small_shapes(ab, mels, D, H, L, enc, B, T):
+    """Widths with 1, 3, 5, 6, 8 channel tiles (the persistent kernels then change channel tile between units), T below one
+    tile, 128 mels: relative criteria only (max-abs scales with the activations' range)."""
+    sd = oracle.random_encoder_state_dict(mels, D, L, enc, seed=D, perturb=True)
+    x = torch.randn(B, mels, T, generator=torch.Generator().manual_seed(T))
+    ref = oracle.audio_encoder_forward(sd, x, H)
+    y = _enc(ab, sd, mels, D, H, L, enc, "bf16")(x.cuda()).float().cpu()
+    d = (y - ref).abs()
+    assert not torch.isnan(y).any()
+    assert float(d.max() / ref.abs().max()) <= 1.3e-2
+    assert float((d > 2e-2 + 1e-2 * ref.abs()).float().mean()) <= 4e-4
+
+
 def test_weight_update_invalidates_the_packed_copy(ab):
     sd = oracle.random_encoder_state_dict(80, 128, 1, False, seed=8, perturb=True)
     m = _enc(ab, sd, 80, 128, 4, 1, False, "fp32")
