@@ -8,6 +8,7 @@ import pytest
 import torch
 
 import oracle
+from oracle.encoder import sinusoids as oracle_sinusoids
 from asr_model_b200 import synth
 
 pytestmark = pytest.mark.gpu
@@ -66,6 +67,32 @@ def test_bf16_variant_within_tolerance(ab, D, H, L, enc, B, T, perturb):
     assert y.dtype == torch.bfloat16 and y.shape == ref.shape
     err = (y.float().cpu() - ref).abs()
     _check_bf16(err, ref, f"D={D} enc={enc} perturb={perturb}")
+
+
+def test_full_size_64x30s_batch_properties(ab):
+    """BASELINE config 2 at full size (64 x 30 s, D=512, L=4, bf16, fused PCM -> hidden): two utterances against the oracle,
+    plus size-independent properties: an utterance alone equals the same utterance inside the batch bit for bit (no
+    cross-utterance coupling: per-utterance floor, tile halos, persistent-loop wrap), a silent clip maps every frame but the
+    edges to one vector, and nothing is left unwritten."""
+    from asr_model_b200.frontend import LogMel
+    N, B = 480000, 64
+    sd = oracle.random_encoder_state_dict(80, 512, 4, False, seed=0, perturb=False)
+    m = _enc(ab, sd, 80, 512, 4, 4, False, "bf16")
+    fe = LogMel(80, 400)
+    classes = ("WHT" * 22)[:B - 1] + "Z"
+    waves = torch.stack([synth.make_wave(c, N, seed=100 + i) for i, c in enumerate(classes)])
+    out = torch.full((B, 3001, 512), float("nan"), device="cuda", dtype=torch.bfloat16)
+    m.forward_pcm(waves.cuda(), fe, out=out)
+    assert not torch.isnan(out.float()).any()
+    for i in (0, 40):                                                     # a W and an H clip against the oracle
+        ref = oracle.audio_encoder_forward(sd, oracle.log_mel_batch(waves[i:i + 1], 80, 400), 4)
+        _check_bf16((out[i:i + 1].float().cpu() - ref).abs(), ref, f"full size, utterance {i}")
+    for i in (1, 17, 63):
+        alone = m.forward_pcm(waves[i:i + 1].cuda(), fe)
+        assert torch.equal(alone[0], out[i]), i
+    z = out[63].float()                                                   # silence: constant log-mel -> translation invariant interior
+    inner = z[64:-64] - torch.from_numpy(oracle_sinusoids(3001, 512).numpy())[64:-64].cuda()
+    assert float((inner - inner[0]).abs().max()) <= 2.5e-2                # one bf16 rounding of values up to ~4
 
 
 def _check_bf16(err, ref, what, scale=1.0):
