@@ -77,7 +77,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParams p) 
     auto pv_done = [&](int s) { return bar0 + 8u * (13 + s); };
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // provably warp-uniform role index
     const int q0 = blockIdx.x * BM, h = blockIdx.y, b = blockIdx.z;
     const int n_kv = p.n_kv;
 

@@ -38,7 +38,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     auto xbar = [&](int a) { return bar0 + 8u * (2 * STAGES + 4 + a); };
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 6);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // provably warp-uniform role index
     constexpr bool is_ln = EPI == TC_LN;
     const int cl = is_ln ? p.cluster : 1;                                    // CTAs per cluster (cluster LayerNorm)
     const uint32_t crank = cl > 1 ? cluster_ctarank() : 0;

@@ -196,7 +196,7 @@ gemm_tct_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
     auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * STAGES + 2 + a); };
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // provably warp-uniform role index
     const int units = p.m_tiles * p.n_ct;
     const int kb_main = p.K / BK;
     const int num_kb = kb_main + (RES ? 2 : 0);
