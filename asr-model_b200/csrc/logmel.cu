@@ -118,7 +118,7 @@ logmel_kernel(const LogmelParams p, int tiles_per_utt, int total_tiles) {
 
     const int g = tid / R, j = tid - g * R;
     float2* yg = s_y + g * C::YSTRIDE;
-    const int lane = tid & 31, warp = tid >> 5;
+    const int lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // provably warp-uniform: filter loops run on the uniform datapath
     constexpr int nwarp = C::THREADS / 32;
     constexpr int FW = FB < 32 ? FB : 32;                   // frames handled by one warp pass
     constexpr int MSUB = 32 / FW;                           // filters handled side by side
