@@ -360,17 +360,20 @@ gemm_tct_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
                 if ((it & 1) != (g >> 1)) continue;         // the other team's unit
                 mbar_wait_backoff(tfull_bar(a), aph, 32, 256);
                 tc_fence_after();
-#pragma unroll 1
-                for (int pass = 0; pass < 2; ++pass) {
-                    const int ws = 28 * ((g & 1) * 2 + pass), tw = tb + ws;
-                    float h[44];
-                    {   // GLU: (v + bv) * sigmoid(g + bg) = hv + hv tanh((g + bg) / 2),  hv = (v + bv) / 2
+                float h[44];
+                auto glu = [&](float v, float gate) {       // (v + bv) * sigmoid(gate + bg) = hv + hv tanh((gate + bg) / 2), hv = (v + bv) / 2
+                    const float hv = fmaf(v, 0.5f, hb0);
+                    return fmaf(hv, tanh_approx(fmaf(gate, 0.5f, hb1)), hv);
+                };
+                {   // pass 0: the 44-column window of the warp's first group
+                    const int ws = 28 * ((g & 1) * 2), tw = tb + ws;
+                    {
                         float gt[32];
                         tmem_ld32_nw(acc + ws, h);
                         tmem_ld32_nw(acc + 128 + ws, gt);
                         tmem_ld_wait();
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) { const float hv = fmaf(h[i], 0.5f, hb0); h[i] = fmaf(hv, tanh_approx(fmaf(gt[i], 0.5f, hb1)), hv); }
+                        for (int i = 0; i < 32; ++i) h[i] = glu(h[i], gt[i]);
                     }
                     {
                         float gt[12];
@@ -379,12 +382,29 @@ gemm_tct_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
                         tmem_ld8_nw(acc + 128 + ws + 32, gt);
                         tmem_ld4_nw(acc + 128 + ws + 40, gt + 8);
                         tmem_ld_wait();
-                        if (pass == 1) { tc_fence_before(); mbar_arrive(tempty_bar(a)); }   // this warp's last TMEM read of the unit
 #pragma unroll
-                        for (int i = 0; i < 12; ++i) { const float hv = fmaf(h[32 + i], 0.5f, hb0); h[32 + i] = fmaf(hv, tanh_approx(fmaf(gt[i], 0.5f, hb1)), hv); }
+                        for (int i = 0; i < 12; ++i) h[32 + i] = glu(h[32 + i], gt[i]);
                     }
-                    const int t0 = tw + 8;                  // frame of output 0 (>= 0)
-                    __nv_bfloat16* op = p.out + (row0 + t0) * ld + c;
+                    __nv_bfloat16* op = p.out + (row0 + tw + 8) * ld + c;
+                    if (tw >= 0 && tw + 43 < p.T) dw15_emit<false, NO, ACT2>(h, k, op, ld, tw, p.T);
+                    else dw15_emit<true, NO, ACT2>(h, k, op, ld, tw, p.T);
+                }
+                {   // pass 1: the next group's window starts 28 columns on -- its first 16 GLU values are pass 0's last 16
+                    const int ws = 28 * ((g & 1) * 2 + 1), tw = tb + ws;
+                    // (frames outside [0, T) were zeroed by pass 0's masked path under the very rule pass 1 applies)
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) h[i] = h[i + 28];
+                    float gt[28];
+                    tmem_ld8_nw(acc + ws + 16, h + 16); tmem_ld8_nw(acc + ws + 24, h + 24); tmem_ld8_nw(acc + ws + 32, h + 32);
+                    tmem_ld4_nw(acc + ws + 40, h + 40);
+                    tmem_ld8_nw(acc + 128 + ws + 16, gt); tmem_ld8_nw(acc + 128 + ws + 24, gt + 8); tmem_ld8_nw(acc + 128 + ws + 32, gt + 16);
+                    tmem_ld4_nw(acc + 128 + ws + 40, gt + 24);
+                    tmem_ld_wait();
+                    tc_fence_before();
+                    mbar_arrive(tempty_bar(a));             // this warp's last TMEM read of the unit
+#pragma unroll
+                    for (int i = 0; i < 28; ++i) h[16 + i] = glu(h[16 + i], gt[i]);
+                    __nv_bfloat16* op = p.out + (row0 + tw + 8) * ld + c;
                     if (tw >= 0 && tw + 43 < p.T) dw15_emit<false, NO, ACT2>(h, k, op, ld, tw, p.T);
                     else dw15_emit<true, NO, ACT2>(h, k, op, ld, tw, p.T);
                 }
