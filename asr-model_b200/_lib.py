@@ -8,7 +8,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libasrb200.so")
 
-OK, F32, BF16 = 0, 0, 1
+OK, F32, BF16, F16 = 0, 0, 1, 2
 _lib = None
 
 
@@ -26,6 +26,7 @@ _vp, _i64, _i32, _sz, _int = C.c_void_p, C.c_int64, C.c_int32, C.c_size_t, C.c_i
 _pp = C.POINTER(C.c_void_p)
 SYMBOLS = {
     "asrb_version": (_int, []),
+    "asrb_operand_format": (_int, []),
     "asrb_last_error": (C.c_char_p, []),
     "asrb_device_check": (_int, [_int]),
     "asrb_logmel_plan_create": (_int, [_int, _int, _int, _vp, _vp, _pp]),
@@ -73,6 +74,12 @@ def load():
         raise AsrbError(f"libasrb200.so version {lib.asrb_version()} != header 100")
     _lib = lib
     return lib
+
+
+def operand_dtype():
+    """torch dtype of the tensor-core variant's MMA operands (include/asrb200.h: asrb_operand_format)."""
+    import torch
+    return torch.float16 if load().asrb_operand_format() == F16 else torch.bfloat16
 
 
 def check(code: int, what: str = ""):

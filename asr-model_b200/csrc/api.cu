@@ -62,6 +62,7 @@ extern "C" int asrb_profile_get(int i, const char** tag, float* ms, double* flop
 }
 
 extern "C" int asrb_version(void) { return ASRB_VERSION; }
+extern "C" int asrb_operand_format(void) { return ASRB_OP16_IS_F16 ? ASRB_F16 : ASRB_BF16; }
 extern "C" const char* asrb_last_error(void) { return asrb::err_slot().c_str(); }
 extern "C" int asrb_device_check(int device) {
     int prev = 0;

@@ -1,14 +1,14 @@
 // Flash-style softmax attention on tcgen05 / TMEM for the optional TransformerEncoderLayer
 // (model.py:138,163: nn.MultiheadAttention, no mask, non-causal, softmax(q k^T / sqrt(hd)) v).
 //
-// One CTA = one (utterance, head, 128-query tile).  qkv is the packed bf16 [B][T][3D] output of
+// One CTA = one (utterance, head, 128-query tile).  qkv is the packed op16 (16-bit operand format, common.cuh) [B][T][3D] output of
 // the in_proj GEMM; Q, K and V tiles arrive by TMA (3-D map, OOB rows zero filled).
 //   warp 0      TMA producer: Q once, then a 2-deep ring of K tiles and a 2-deep ring of V tiles
 //   warp 1      MMA issuer:   S_j = Q K_j^T (SS, both K-major)  ->  TMEM S[j&1] (128 fp32 columns)
 //                             O  += P_j V_j (A = P in smem K-major, B = V in smem MN-major) -> TMEM O
 //   warps 2..5  softmax:      thread = query row (TMEM lane); online softmax in the exp2 domain with
 //                             a stale running max (O is rescaled in TMEM only when the max grew by
-//                             more than 2^8), P_j -> bf16 -> swizzled smem, final O / l -> out bf16.
+//                             more than 2^8), P_j -> op16 -> swizzled smem, final O / l -> out op16.
 // S is never written to HBM; scores and probabilities live in TMEM / shared memory only.
 #include "tc_common.cuh"
 
@@ -18,13 +18,13 @@ template <int HD> struct AttnCfg {
     static constexpr int SUB = HD / 64;                          // 64-column sub-tiles per head_dim
     static constexpr int Q_BYTES = BM * HD * 2;
     static constexpr int KV_BYTES = BM * HD * 2;                 // one K (or V) tile: 128 keys x HD
-    static constexpr int P_BYTES = BM * BM * 2;                  // 128 queries x 128 keys bf16
+    static constexpr int P_BYTES = BM * BM * 2;                  // 128 queries x 128 keys, 16-bit
     static constexpr int SMEM = Q_BYTES + 4 * KV_BYTES + 2 * P_BYTES + 256;
     static constexpr int THREADS = 192;
     static_assert(SMEM <= 227 * 1024, "shared memory budget");
 };
 
-struct AttnParams { int T, D, H, n_kv; float scale_log2; __nv_bfloat16* out; };
+struct AttnParams { int T, D, H, n_kv; float scale_log2; op16* out; };
 
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) {
     const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
@@ -46,7 +46,7 @@ __device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t saddr, uint32_t l
            (1ull << 46) | (2ull << 61);
 }
 __host__ __device__ constexpr uint32_t make_idesc_ex(int n, bool b_mn_major) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((b_mn_major ? 1u : 0u) << 16) | ((uint32_t)(n >> 3) << 17) |
+    return (1u << 4) | (ASRB_OP16_IS_F16 ? 0u : ((1u << 7) | (1u << 10))) | ((b_mn_major ? 1u : 0u) << 16) | ((uint32_t)(n >> 3) << 17) |
            ((uint32_t)(BM >> 4) << 24);
 }
 __device__ __forceinline__ float ex2f(float x) {
@@ -204,7 +204,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParams p) 
                 l *= factor;
                 m_used = m_new;
             }
-            // ---- pass B: p = 2^(s - m_used), row sum, P -> bf16 -> swizzled smem (A operand of P V) ----
+            // ---- pass B: p = 2^(s - m_used), row sum, P -> op16 -> swizzled smem (A operand of P V) ----
             if (j >= 2) mbar_wait(pv_done(st), (uint32_t)((j - 2) >> 1) & 1u);          // P buffer st is free again
             unsigned char* pbuf = s_p + st * C::P_BYTES;
 #pragma unroll
@@ -224,10 +224,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParams p) 
                 for (int i = 0; i < 4; ++i) {
                     const int chunk = ((c & 32) >> 3) + i;
                     uint4 q;
-                    __nv_bfloat162 h0 = __floats2bfloat162_rn(v[8 * i + 0], v[8 * i + 1]), h1 = __floats2bfloat162_rn(v[8 * i + 2], v[8 * i + 3]);
-                    __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * i + 4], v[8 * i + 5]), h3 = __floats2bfloat162_rn(v[8 * i + 6], v[8 * i + 7]);
-                    q.x = *reinterpret_cast<uint32_t*>(&h0); q.y = *reinterpret_cast<uint32_t*>(&h1);
-                    q.z = *reinterpret_cast<uint32_t*>(&h2); q.w = *reinterpret_cast<uint32_t*>(&h3);
+                    q.x = pack_op16x2(v[8 * i + 0], v[8 * i + 1]); q.y = pack_op16x2(v[8 * i + 2], v[8 * i + 3]);
+                    q.z = pack_op16x2(v[8 * i + 4], v[8 * i + 5]); q.w = pack_op16x2(v[8 * i + 6], v[8 * i + 7]);
                     *reinterpret_cast<uint4*>(sub + ((chunk ^ (r & 7)) << 4)) = q;
                 }
             }
@@ -235,7 +233,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParams p) 
             tc_fence_before();
             mbar_arrive(p_ready(st));
         }
-        // ---- epilogue: O / l -> bf16 -> out[b, q0 + r, h*HD ...] ----
+        // ---- epilogue: O / l -> op16 -> out[b, q0 + r, h*HD ...] ----
         mbar_wait(pv_done((n_kv - 1) & 1), (uint32_t)((n_kv - 1) >> 1) & 1u);
         tc_fence_after();
         const float inv = 1.0f / l;
@@ -245,14 +243,12 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParams p) 
             float o[32];
             tmem_ld32(tm_o + lane_off + c, o);
             if (t < p.T) {
-                __nv_bfloat16* dst = p.out + ((int64_t)b * p.T + t) * p.D + h * HD + c;
+                op16* dst = p.out + ((int64_t)b * p.T + t) * p.D + h * HD + c;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     uint4 q;
-                    __nv_bfloat162 h0 = __floats2bfloat162_rn(o[8 * i + 0] * inv, o[8 * i + 1] * inv), h1 = __floats2bfloat162_rn(o[8 * i + 2] * inv, o[8 * i + 3] * inv);
-                    __nv_bfloat162 h2 = __floats2bfloat162_rn(o[8 * i + 4] * inv, o[8 * i + 5] * inv), h3 = __floats2bfloat162_rn(o[8 * i + 6] * inv, o[8 * i + 7] * inv);
-                    q.x = *reinterpret_cast<uint32_t*>(&h0); q.y = *reinterpret_cast<uint32_t*>(&h1);
-                    q.z = *reinterpret_cast<uint32_t*>(&h2); q.w = *reinterpret_cast<uint32_t*>(&h3);
+                    q.x = pack_op16x2(o[8 * i + 0] * inv, o[8 * i + 1] * inv); q.y = pack_op16x2(o[8 * i + 2] * inv, o[8 * i + 3] * inv);
+                    q.z = pack_op16x2(o[8 * i + 4] * inv, o[8 * i + 5] * inv); q.w = pack_op16x2(o[8 * i + 6] * inv, o[8 * i + 7] * inv);
                     *reinterpret_cast<uint4*>(dst + 8 * i) = q;
                 }
             }
@@ -282,7 +278,7 @@ static int launch_attn(const CUtensorMap& map, const AttnParams& p, int64_t B, c
     return ASRB_OK;
 }
 
-// qkv [B][T][3D] bf16 (q | k | v) -> out [B][T][D] bf16, softmax(q k^T * scale) v per head.
+// qkv [B][T][3D] op16 (q | k | v) -> out [B][T][D] op16, softmax(q k^T * scale) v per head.
 int launch_attention_tc(const void* qkv, void* out, int64_t B, int64_t T, int D, int H, float scale, cudaStream_t st) {
     if (!attention_tc_supported(D, H)) return fail(ASRB_E_ARG, "tcgen05 attention: head_dim %d unsupported (64 or 128)", H ? D / H : 0);
     if (B <= 0 || T <= 0) return ASRB_OK;
@@ -291,7 +287,7 @@ int launch_attention_tc(const void* qkv, void* out, int64_t B, int64_t T, int D,
     ASRB_TRY(make_act_map(&map, qkv, B, T, 3 * D));
     AttnParams p;
     p.T = (int)T; p.D = D; p.H = H; p.n_kv = (int)((T + BM - 1) / BM);
-    p.scale_log2 = scale * 1.4426950408889634f; p.out = (__nv_bfloat16*)out;
+    p.scale_log2 = scale * 1.4426950408889634f; p.out = (op16*)out;
     ProfScope ps("attention_tc", st, 4.0 * B * (double)T * T * D, 2.0 * B * T * D * 4.0);
     if (D / H == 128) return launch_attn<128>(map, p, B, st);
     return launch_attn<64>(map, p, B, st);

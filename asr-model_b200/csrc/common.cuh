@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
@@ -104,6 +105,13 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
+// valid samples of utterance b: lengths[b] clamped to [0, n_samples] (a bad length must not read or write out of bounds)
+__device__ __forceinline__ int64_t clamp_len(const int32_t* lengths, int b, int64_t n_samples) {
+    if (!lengths) return n_samples;
+    const int64_t l = (int64_t)lengths[b];
+    return l < 0 ? 0 : (l > n_samples ? n_samples : l);
+}
+
 // order-preserving float <-> uint32 key (for atomicMax on floats of either sign)
 __device__ __forceinline__ uint32_t f2key(float f) {
     uint32_t b = __float_as_uint(f);
@@ -111,6 +119,60 @@ __device__ __forceinline__ uint32_t f2key(float f) {
 }
 __device__ __forceinline__ float key2f(uint32_t k) {
     return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+// ---- the 16-bit tensor-core operand format ------------------------------------------------
+// Every MMA operand that lives in HBM or shared memory (activations X / Y / U / QKV / P / FFN hidden and the packed
+// weights) is IEEE fp16, accumulated in fp32 by tcgen05.mma kind::f16; hidden states leave the encoder as bf16.
+// Why not bf16 operands: with 8 mantissa bits per operand the encoder cannot meet allclose(atol 2e-2, rtol 1e-2)
+// against the fp32 reference -- not even with the whole last layer computed exactly (tools/numerics_study.py:
+// worst error / tolerance 1.5-2.7 for bf16 operands, 0.23-0.43 for fp16 at the same MMA rate and the same bytes).
+// Range: every operand is either a LayerNorm / GELU / SiLU / softmax output or a weight; conversions saturate
+// (cvt.rn.satfinite) instead of producing inf.  -DASRB_OPERAND_BF16 rebuilds the library with bf16 operands for A/B runs.
+#ifdef ASRB_OPERAND_BF16
+typedef __nv_bfloat16 op16;
+#define ASRB_OP16_IS_F16 0
+#else
+typedef __half op16;
+#define ASRB_OP16_IS_F16 1
+#endif
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {           // a -> low half
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
+}
+__device__ __forceinline__ uint32_t pack_op16x2(float a, float b) {           // two fp32 -> packed operand pair, a -> low half
+#if ASRB_OP16_IS_F16
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
+#else
+    return pack_bf16x2(a, b);
+#endif
+}
+__device__ __forceinline__ float2 unpack_op16x2(uint32_t u) {
+#if ASRB_OP16_IS_F16
+    return __half22float2(*reinterpret_cast<const __half2*>(&u));
+#else
+    return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u));
+#endif
+}
+__device__ __forceinline__ op16 to_op16(float v) {
+#if ASRB_OP16_IS_F16
+    unsigned short r;
+    asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(r) : "f"(v));
+    return __ushort_as_half(r);
+#else
+    return __float2bfloat16_rn(v);
+#endif
+}
+inline op16 host_to_op16(float v) {
+#if ASRB_OP16_IS_F16
+    const float lim = 65504.0f;
+    return __float2half_rn(v > lim ? lim : (v < -lim ? -lim : v));
+#else
+    return __float2bfloat16_rn(v);
+#endif
 }
 
 template <class T> struct io;
@@ -121,6 +183,14 @@ template <> struct io<float> {
 template <> struct io<__nv_bfloat16> {
     __device__ static float ld(const __nv_bfloat16* p) { return __bfloat162float(*p); }
     __device__ static void st(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+};
+template <> struct io<__half> {
+    __device__ static float ld(const __half* p) { return __half2float(*p); }
+    __device__ static void st(__half* p, float v) {
+        unsigned short r;
+        asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(r) : "f"(v));
+        *p = __ushort_as_half(r);
+    }
 };
 
 }  // namespace asrb

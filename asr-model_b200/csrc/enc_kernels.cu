@@ -1,6 +1,6 @@
 // CUDA-core kernels of the encoder: the fp32 (1e-4) variant's GEMM, and the streaming ops
 // both variants share (layout change, LayerNorm, GLU, depthwise convs, attention, rotary).
-// All math is fp32; storage is fp32 or bf16 per tensor.  Channels-last everywhere.
+// All math is fp32; storage is fp32 or the 16-bit operand format (op16, common.cuh) per tensor.  Channels-last everywhere.
 #include "enc_kernels.cuh"
 
 namespace asrb {
@@ -20,8 +20,7 @@ __global__ void to_channels_last_kernel(float* src, TO* dst, int C, int CP, int6
     int64_t Tb = T;
     if (keys) {
         floor_s = ((key2f(keys[b]) - 8.0f) + 4.0f) / 4.0f;
-        const int64_t len = lengths ? (int64_t)lengths[b] : n_samples;
-        Tb = 1 + len / hop;
+        Tb = 1 + clamp_len(lengths, b, n_samples) / hop;
     }
     float* s = src + (int64_t)b * C * T;
     for (int c = warp; c < C; c += nwarp) {
@@ -50,7 +49,7 @@ int launch_to_channels_last(const float* src, void* dst, DType dt, int64_t B, in
     if (dt == DT_F32)
         to_channels_last_kernel<float><<<grid, 256, smem, st>>>((float*)src, (float*)dst, C, CP, T, keys, lengths, n_samples, hop, fix_src);
     else
-        to_channels_last_kernel<__nv_bfloat16><<<grid, 256, smem, st>>>((float*)src, (__nv_bfloat16*)dst, C, CP, T, keys, lengths, n_samples, hop, fix_src);
+        to_channels_last_kernel<op16><<<grid, 256, smem, st>>>((float*)src, (op16*)dst, C, CP, T, keys, lengths, n_samples, hop, fix_src);
     ASRB_LAUNCH_CHECK();
     return ASRB_OK;
 }
@@ -132,12 +131,13 @@ int launch_gemm_simt(const void* A, DType a_dt, const float* W, const float* bia
     dim3 grid((unsigned)((T + 63) / 64), (unsigned)((N + 63) / 64), (unsigned)B);
     if (a_dt == DT_F32 && o_dt == DT_F32)
         gemm_simt_kernel<float, float><<<grid, 256, 0, st>>>((const float*)A, W, bias, (const float*)res, (float*)out, T, K, N, taps, act);
-    else if (a_dt == DT_F32 && o_dt == DT_BF16)
-        gemm_simt_kernel<float, __nv_bfloat16><<<grid, 256, 0, st>>>((const float*)A, W, bias, (const __nv_bfloat16*)res, (__nv_bfloat16*)out, T, K, N, taps, act);
-    else if (a_dt == DT_BF16 && o_dt == DT_BF16)
-        gemm_simt_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)A, W, bias, (const __nv_bfloat16*)res, (__nv_bfloat16*)out, T, K, N, taps, act);
-    else
-        gemm_simt_kernel<__nv_bfloat16, float><<<grid, 256, 0, st>>>((const __nv_bfloat16*)A, W, bias, (const float*)res, (float*)out, T, K, N, taps, act);
+    else if (a_dt == DT_F32 && o_dt == DT_OP16)
+        gemm_simt_kernel<float, op16><<<grid, 256, 0, st>>>((const float*)A, W, bias, (const op16*)res, (op16*)out, T, K, N, taps, act);
+    else if (a_dt == DT_OP16 && o_dt == DT_OP16)
+        gemm_simt_kernel<op16, op16><<<grid, 256, 0, st>>>((const op16*)A, W, bias, (const op16*)res, (op16*)out, T, K, N, taps, act);
+    else if (a_dt == DT_OP16 && o_dt == DT_F32)
+        gemm_simt_kernel<op16, float><<<grid, 256, 0, st>>>((const op16*)A, W, bias, (const float*)res, (float*)out, T, K, N, taps, act);
+    else return fail(ASRB_E_ARG, "gemm_simt: storage types %d -> %d unsupported", (int)a_dt, (int)o_dt);
     ASRB_LAUNCH_CHECK();
     return ASRB_OK;
 }
@@ -145,10 +145,10 @@ int launch_gemm_simt(const void* A, DType a_dt, const float* W, const float* bia
 // ------------------------------------------------------------------------------------------
 // LayerNorm over the channel dim (essentials.py:102-113 / nn.LayerNorm), one warp per row
 // ------------------------------------------------------------------------------------------
-template <class T>
+template <class T, class TO>
 __global__ void layernorm_kernel(const T* __restrict__ x, const T* __restrict__ res,
                                  const float* __restrict__ gamma, const float* __restrict__ beta,
-                                 T* __restrict__ out, int64_t rows, int D, float eps) {
+                                 TO* __restrict__ out, int64_t rows, int D, float eps) {
     const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) return;
     const int lane = threadIdx.x & 31;
@@ -170,19 +170,25 @@ __global__ void layernorm_kernel(const T* __restrict__ x, const T* __restrict__ 
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
         const int c = i * 32 + lane;
-        if (c < D) io<T>::st(out + row * D + c, (v[i] - mean) * rstd * gamma[c] + beta[c]);
+        if (c < D) io<TO>::st(out + row * D + c, (v[i] - mean) * rstd * gamma[c] + beta[c]);
     }
 }
 
 int launch_layernorm(const void* x, const void* res, const float* gamma, const float* beta, void* out,
-                     DType dt, int64_t rows, int D, float eps, cudaStream_t st) {
+                     DType dt, int64_t rows, int D, float eps, cudaStream_t st, DType o_dt) {
+    if (o_dt == DT_SAME) o_dt = dt;
     if (D > 1024) return fail(ASRB_E_ARG, "layernorm: D=%d > 1024", D);
     ProfScope ps("layernorm", st, 0.0, (double)rows * D * (dt == DT_F32 ? 4.0 : 2.0) * (res ? 3.0 : 2.0));
     const unsigned grid = (unsigned)((rows + 7) / 8);
-    if (dt == DT_F32)
-        layernorm_kernel<float><<<grid, 256, 0, st>>>((const float*)x, (const float*)res, gamma, beta, (float*)out, rows, D, eps);
-    else
-        layernorm_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)res, gamma, beta, (__nv_bfloat16*)out, rows, D, eps);
+    if (dt == DT_F32 && o_dt == DT_F32)
+        layernorm_kernel<float, float><<<grid, 256, 0, st>>>((const float*)x, (const float*)res, gamma, beta, (float*)out, rows, D, eps);
+    else if (dt == DT_OP16 && o_dt == DT_OP16)
+        layernorm_kernel<op16, op16><<<grid, 256, 0, st>>>((const op16*)x, (const op16*)res, gamma, beta, (op16*)out, rows, D, eps);
+    else if (dt == DT_OP16 && o_dt == DT_BF16)
+        layernorm_kernel<op16, __nv_bfloat16><<<grid, 256, 0, st>>>((const op16*)x, (const op16*)res, gamma, beta, (__nv_bfloat16*)out, rows, D, eps);
+    else if (dt == DT_OP16 && o_dt == DT_F32)
+        layernorm_kernel<op16, float><<<grid, 256, 0, st>>>((const op16*)x, (const op16*)res, gamma, beta, (float*)out, rows, D, eps);
+    else return fail(ASRB_E_ARG, "layernorm: storage types %d -> %d unsupported", (int)dt, (int)o_dt);
     ASRB_LAUNCH_CHECK();
     return ASRB_OK;
 }
@@ -206,7 +212,7 @@ int launch_glu(const void* x, void* out, DType dt, int64_t rows, int D, cudaStre
     unsigned grid = (unsigned)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
     if (grid == 0) grid = 1;
     if (dt == DT_F32) glu_kernel<float><<<grid, 256, 0, st>>>((const float*)x, (float*)out, rows, D);
-    else glu_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)out, rows, D);
+    else glu_kernel<op16><<<grid, 256, 0, st>>>((const op16*)x, (op16*)out, rows, D);
     ASRB_LAUNCH_CHECK();
     return ASRB_OK;
 }
@@ -220,9 +226,9 @@ template <> struct pair_io<float> {
     __device__ static float2 ld(const float* p) { return *reinterpret_cast<const float2*>(p); }
     __device__ static void st(float* p, float2 v) { *reinterpret_cast<float2*>(p) = v; }
 };
-template <> struct pair_io<__nv_bfloat16> {
-    __device__ static float2 ld(const __nv_bfloat16* p) { return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p)); }
-    __device__ static void st(__nv_bfloat16* p, float2 v) { *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(v.x, v.y); }
+template <> struct pair_io<op16> {
+    __device__ static float2 ld(const op16* p) { return unpack_op16x2(*reinterpret_cast<const uint32_t*>(p)); }
+    __device__ static void st(op16* p, float2 v) { *reinterpret_cast<uint32_t*>(p) = pack_op16x2(v.x, v.y); }
 };
 
 template <bool FAST> __device__ __forceinline__ float dw_act(float v, int act) {
@@ -263,9 +269,9 @@ dwconv_kernel(const TI* __restrict__ x, const float* __restrict__ w, const float
 #pragma unroll
                 for (int j = 0; j < VEC; ++j) vals[j] = f[j];
             } else {
-                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+                const uint32_t* h = reinterpret_cast<const uint32_t*>(&q);
 #pragma unroll
-                for (int j = 0; j < VEC / 2; ++j) { const float2 f = __bfloat1622float2(h[j]); vals[2 * j] = f.x; vals[2 * j + 1] = f.y; }
+                for (int j = 0; j < VEC / 2; ++j) { const float2 f = unpack_op16x2(h[j]); vals[2 * j] = f.x; vals[2 * j + 1] = f.y; }
             }
         } else {
 #pragma unroll
@@ -338,9 +344,10 @@ int launch_dwconv(const void* x, DType x_dt, const float* w, const float* bias, 
     ProfScope ps(KW == 15 ? "dwconv15_bn_silu" : (pos ? "dwconv3_gelu_pos" : "dwconv3_gelu"), st, 2.0 * B * T * (double)D * KW,
                  (double)B * T * D * ((x_dt == DT_F32 ? 4.0 : 2.0) + (o_dt == DT_F32 ? 4.0 : 2.0)));
     if (x_dt == DT_F32 && o_dt == DT_F32) return dwconv_dispatch<float, float>(x, w, bias, out, B, T, D, KW, act, pos, fast, st, out32);
-    if (x_dt == DT_BF16 && o_dt == DT_BF16) return dwconv_dispatch<__nv_bfloat16, __nv_bfloat16>(x, w, bias, out, B, T, D, KW, act, pos, fast, st, out32);
-    if (x_dt == DT_BF16 && o_dt == DT_F32) return dwconv_dispatch<__nv_bfloat16, float>(x, w, bias, out, B, T, D, KW, act, pos, fast, st, out32);
-    return dwconv_dispatch<float, __nv_bfloat16>(x, w, bias, out, B, T, D, KW, act, pos, fast, st, out32);
+    if (x_dt == DT_OP16 && o_dt == DT_OP16) return dwconv_dispatch<op16, op16>(x, w, bias, out, B, T, D, KW, act, pos, fast, st, out32);
+    if (x_dt == DT_OP16 && o_dt == DT_F32) return dwconv_dispatch<op16, float>(x, w, bias, out, B, T, D, KW, act, pos, fast, st, out32);
+    if (x_dt == DT_F32 && o_dt == DT_OP16) return dwconv_dispatch<float, op16>(x, w, bias, out, B, T, D, KW, act, pos, fast, st, out32);
+    return fail(ASRB_E_ARG, "dwconv: storage types %d -> %d unsupported", (int)x_dt, (int)o_dt);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -431,7 +438,7 @@ int launch_attention_simt_ex(const void* q, const void* k, const void* v, int64_
                              void* out, DType dt, int64_t B, int64_t T, int D, int H, float scale, cudaStream_t st) {
     ProfScope ps("attention_simt", st, 4.0 * B * (double)T * T * D, (double)B * T * D * 4.0 * (dt == DT_F32 ? 4.0 : 2.0));
     if (dt == DT_F32) return attention_dispatch<float>(q, k, v, ldq, ldk, ldv, out, B, T, D, H, scale, st);
-    return attention_dispatch<__nv_bfloat16>(q, k, v, ldq, ldk, ldv, out, B, T, D, H, scale, st);
+    return attention_dispatch<op16>(q, k, v, ldq, ldk, ldv, out, B, T, D, H, scale, st);
 }
 
 int launch_attention_simt(const void* qkv, void* out, DType dt, int64_t B, int64_t T, int D, int H, float scale,

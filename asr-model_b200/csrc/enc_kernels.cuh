@@ -6,7 +6,8 @@
 namespace asrb {
 
 enum Act { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2, ACT_SILU = 3, ACT_GELU_GELU = 4 };
-enum DType { DT_F32 = ASRB_F32, DT_BF16 = ASRB_BF16 };
+// storage types: fp32, bf16 (hidden states as they leave the encoder), op16 (the tensor-core operand format, common.cuh)
+enum DType { DT_F32 = ASRB_F32, DT_BF16 = ASRB_BF16, DT_OP16 = 2, DT_SAME = -1 };
 
 // ---- CUDA-core kernels (fp32 math; storage type per argument) ----------------------------
 
@@ -25,7 +26,7 @@ int launch_gemm_simt(const void* A, DType a_dt, const float* W, const float* bia
 
 // out[r,:] = LayerNorm(x[r,:] (+ res[r,:])) * gamma + beta   (biased variance, eps)
 int launch_layernorm(const void* x, const void* res, const float* gamma, const float* beta, void* out,
-                     DType dt, int64_t rows, int D, float eps, cudaStream_t st);
+                     DType dt, int64_t rows, int D, float eps, cudaStream_t st, DType o_dt = DT_SAME);
 
 // GLU over the channel dim: x [rows][2D] -> out [rows][D] = x[:, :D] * sigmoid(x[:, D:])
 int launch_glu(const void* x, void* out, DType dt, int64_t rows, int D, cudaStream_t st);
@@ -47,7 +48,7 @@ int launch_attention_simt_ex(const void* q, const void* k, const void* v, int64_
                              void* out, DType dt, int64_t B, int64_t T, int D, int H, float scale,
                              cudaStream_t st);
 
-// Flash-style attention on tcgen05/TMEM (attn_tc.cu): bf16 qkv [B][T][3D] -> bf16 out [B][T][D]; head_dim 64 | 128
+// Flash-style attention on tcgen05/TMEM (attn_tc.cu): op16 qkv [B][T][3D] -> op16 out [B][T][D]; head_dim 64 | 128
 bool attention_tc_supported(int D, int H);
 int launch_attention_tc(const void* qkv, void* out, int64_t B, int64_t T, int D, int H, float scale, cudaStream_t st);
 
@@ -57,21 +58,21 @@ int launch_rmsnorm(const float* x, const float* w, float* out, int64_t rows, int
 int launch_rotary_headnorm(float* x, int64_t ld, const float* xa, const float* ln_w, const float* freqs,
                            int64_t B, int64_t T, int D, int H, float pre_scale, cudaStream_t st);
 
-// ---- tcgen05 / TMEM / TMA GEMM (gemm_tc.cu), bf16 operands, fp32 accumulate -----------------
+// ---- tcgen05 / TMEM / TMA GEMM (gemm_tc.cu), 16-bit (op16) operands, fp32 accumulate -----------------
 enum TcEpilogue { TC_BIAS_ACT = 0, TC_GLU = 1, TC_RES_ACT = 2, TC_LN = 3,
                   TC_GLU_DW = 4,        // GLU -> depthwise conv down the frames (+folded BN) -> act2
                   TC_RES_ACT_DW = 5 };  // bias + residual + act -> depthwise conv -> act2 (+ sinusoids)
 
 struct TcGemmArgs {
-    const __nv_bfloat16* A;      // [B][T][K] channels-last
-    const __nv_bfloat16* W;      // [N][taps*K] tap-major (GLU: value/gate interleaved per tile)
+    const op16* A;               // [B][T][K] channels-last
+    const op16* W;               // [N][taps*K] tap-major (GLU: value/gate interleaved per tile)
     const float* bias;           // [N]
-    const __nv_bfloat16* res;    // [B][T][Nout] or NULL
+    const op16* res;             // [B][T][Nout] or NULL
     const float* res32;          // TC_LN: fp32 residual instead of res (post-norm residual streams stay fp32)
     float* out32;                // TC_LN: optional fp32 copy of the output
     const float* gamma;          // TC_LN
     const float* beta;           // TC_LN
-    void* out;                   // [B][T][Nout] bf16 (fp32 when out_f32)
+    void* out;                   // [B][T][Nout] op16 (bf16 when out_bf16: the encoder's result; fp32 when out_f32)
     int64_t B, T;
     int K, N, taps;
     int epilogue; int act; float eps;
@@ -79,6 +80,7 @@ struct TcGemmArgs {
     const float* dw_b; int dw_kw; int dw_act;
     const float* pos;            // optional [T][Nout] sinusoid table added after dw_act
     int out_f32;                 // store fp32 (consumer is a depthwise conv, not an MMA); not with TC_LN
+    int out_bf16;                // store bf16: this launch writes the hidden states the caller receives
 };
 bool tc_gemm_supported(int K, int N, int epilogue);
 int  tc_glu_tile_n(int N);                    // BN the GLU weight interleave must use
@@ -86,6 +88,6 @@ int  launch_gemm_tc(const TcGemmArgs& a, cudaStream_t st);
 // channel-major variants of TC_GLU_DW / TC_RES_ACT_DW (gemm_tct.cu): lanes = channels, columns = frames
 bool tct_supported(const TcGemmArgs& a);
 int  launch_gemm_tct(const TcGemmArgs& a, cudaStream_t st);
-const __nv_bfloat16* tct_identity();          // per-device 128 x 128 identity operand (created on first use)
+const op16* tct_identity();          // per-device 128 x 128 identity operand (created on first use)
 
 }  // namespace asrb

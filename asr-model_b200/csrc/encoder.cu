@@ -1,6 +1,7 @@
 // AudioEncoder handle: weight folding/packing at create(), forward orchestration.
 // Mirrors model.py:120-169 (norm=False).  Two compute variants share the op sequence:
-//   ASRB_BF16  tcgen05 GEMMs (gemm_tc.cu) with fused epilogues, bf16 activations in HBM
+//   ASRB_BF16  tcgen05 GEMMs (gemm_tc.cu) with fused epilogues; 16-bit activations in HBM (op16 = IEEE fp16 MMA
+//              operands, common.cuh), hidden states returned as bf16
 //   ASRB_F32   FFMA GEMMs and fp32 activations (the <= 1e-4 variant)
 #include "enc_kernels.cuh"
 #include "logmel.cuh"
@@ -42,19 +43,19 @@ struct DevPool {                      // device constants owned by a handle
     void release() { for (void* p : ptrs) cudaFree(p); ptrs.clear(); }
 };
 
-std::vector<__nv_bfloat16> to_bf16(const std::vector<float>& v) {
-    std::vector<__nv_bfloat16> o(v.size());
-    for (size_t i = 0; i < v.size(); ++i) o[i] = __float2bfloat16_rn(v[i]);
+std::vector<op16> to_bf16(const std::vector<float>& v) {          // fp32 weights -> the 16-bit operand format
+    std::vector<op16> o(v.size());
+    for (size_t i = 0; i < v.size(); ++i) o[i] = host_to_op16(v[i]);
     return o;
 }
 
 struct LayerW {
     // k3 weight-normed conv: [D][3][D] (tap-major K); LN; ConvLite; depthwise k3
-    float* wc_f = nullptr; __nv_bfloat16* wc_h = nullptr; float* bc = nullptr;
+    float* wc_f = nullptr; op16* wc_h = nullptr; float* bc = nullptr;
     float* gamma = nullptr; float* beta = nullptr;
-    float* w1_f = nullptr; __nv_bfloat16* w1_h = nullptr; float* b1 = nullptr; float* b1_glu = nullptr;
+    float* w1_f = nullptr; op16* w1_h = nullptr; float* b1 = nullptr; float* b1_glu = nullptr;
     float* dw15 = nullptr; float* dw15_b = nullptr;          // [15][D], BatchNorm folded
-    float* w2_f = nullptr; __nv_bfloat16* w2_h = nullptr; float* b2 = nullptr;
+    float* w2_f = nullptr; op16* w2_h = nullptr; float* b2 = nullptr;
     float* dw3 = nullptr; float* dw3_b = nullptr;            // [3][D]
 };
 
@@ -64,15 +65,15 @@ struct asrb_encoder {
     asrb_encoder_config cfg;
     int CP;                                                   // conv1 input channels padded to 64
     DevPool pool;
-    float* stem1_f = nullptr; __nv_bfloat16* stem1_h = nullptr; float* stem1_b = nullptr;
+    float* stem1_f = nullptr; op16* stem1_h = nullptr; float* stem1_b = nullptr;
     float* stem2_f = nullptr; float* stem2_b = nullptr;
     std::vector<LayerW> layers;
     float* pos_scales = nullptr;
     // TransformerEncoderLayer
-    float* win_f = nullptr; __nv_bfloat16* win_h = nullptr; float* bin = nullptr;
-    float* wo_f = nullptr; __nv_bfloat16* wo_h = nullptr; float* bo = nullptr;
-    float* wf1_f = nullptr; __nv_bfloat16* wf1_h = nullptr; float* bf1 = nullptr;
-    float* wf2_f = nullptr; __nv_bfloat16* wf2_h = nullptr; float* bf2 = nullptr;
+    float* win_f = nullptr; op16* win_h = nullptr; float* bin = nullptr;
+    float* wo_f = nullptr; op16* wo_h = nullptr; float* bo = nullptr;
+    float* wf1_f = nullptr; op16* wf1_h = nullptr; float* bf1 = nullptr;
+    float* wf2_f = nullptr; op16* wf2_h = nullptr; float* bf2 = nullptr;
     float *n1g = nullptr, *n1b = nullptr, *n2g = nullptr, *n2b = nullptr;
 };
 
@@ -188,7 +189,7 @@ extern "C" int asrb_encoder_create(const asrb_encoder_config* cfg, int n_tensors
         GET(l2, p + "linear2.weight", (int64_t)D * F); GET(lb2, p + "linear2.bias", D);
         GET(g1, p + "norm1.weight", D); GET(h1, p + "norm1.bias", D);
         GET(g2, p + "norm2.weight", D); GET(h2, p + "norm2.bias", D);
-        auto put = [&](const float* w, size_t n, float** f, __nv_bfloat16** h) -> int {
+        auto put = [&](const float* w, size_t n, float** f, op16** h) -> int {
             auto t = vecf(w, n);
             if (bf) { auto hh = to_bf16(t); return e->pool.upload(hh, h); }
             return e->pool.upload(t, f);
@@ -254,30 +255,27 @@ EncBuffers carve(const asrb_encoder* e, int64_t B, int64_t T, void* ws, size_t w
     return b;
 }
 
-__global__ void convert_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int64_t n) {
+template <class TI, class TO>
+__global__ void convert_kernel(const TI* __restrict__ in, TO* __restrict__ out, int64_t n) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-        out[i] = __float2bfloat16_rn(in[i]);
-}
-__global__ void convert_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, int64_t n) {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-        out[i] = __bfloat162float(in[i]);
+        io<TO>::st(out + i, io<TI>::ld(in + i));
 }
 
 // GEMM + LayerNorm on the tensor cores: fused epilogue when the row fits TMEM (N <= 512), else
 // GEMM(+residual) to bf16 followed by the row kernel.
-int tc_gemm_ln(const __nv_bfloat16* A, const __nv_bfloat16* W, const float* bias, const __nv_bfloat16* res,
+int tc_gemm_ln(const op16* A, const op16* W, const float* bias, const op16* res,
                const float* gamma, const float* beta, void* out, void* tmp, int64_t B, int64_t T, int K, int N,
-               int taps, cudaStream_t st, const float* res32 = nullptr, float* out32 = nullptr) {
+               int taps, cudaStream_t st, const float* res32 = nullptr, float* out32 = nullptr, int out_bf16 = 0) {
     TcGemmArgs g{};
     g.A = A; g.W = W; g.bias = bias; g.res = res; g.gamma = gamma; g.beta = beta;
     g.B = B; g.T = T; g.K = K; g.N = N; g.taps = taps; g.act = ACT_NONE; g.eps = 1e-5f;
     if (tc_gemm_supported(K, N, TC_LN)) {
-        g.epilogue = TC_LN; g.out = out; g.res32 = res32; g.out32 = out32;
+        g.epilogue = TC_LN; g.out = out; g.res32 = res32; g.out32 = out32; g.out_bf16 = out_bf16;
         return launch_gemm_tc(g, st);
     }
     g.epilogue = res ? TC_RES_ACT : TC_BIAS_ACT; g.out = tmp;
     ASRB_TRY(launch_gemm_tc(g, st));
-    return launch_layernorm(tmp, nullptr, gamma, beta, out, DT_BF16, B * T, N, 1e-5f, st);
+    return launch_layernorm(tmp, nullptr, gamma, beta, out, DT_OP16, B * T, N, 1e-5f, st, out_bf16 ? DT_BF16 : DT_OP16);
 }
 
 // Stem of one feature stream: conv1 (mels -> D, k3; its input is already in w.a0) or conv2 (1 -> D, k3, straight
@@ -285,7 +283,7 @@ int tc_gemm_ln(const __nv_bfloat16* A, const __nv_bfloat16* W, const float* bias
 int encoder_stem(asrb_encoder* e, const EncBuffers& w, const float* x_c1, int in_ch, int64_t B, int64_t T, void* X, cudaStream_t st) {
     const int D = e->cfg.dims;
     const bool bf = e->cfg.compute == ASRB_BF16;
-    const DType dt = bf ? DT_BF16 : DT_F32;
+    const DType dt = bf ? DT_OP16 : DT_F32;
     const Act stem_act = ACT_GELU;                        // layer 0's leading act_fn (model.py:143)
     if (in_ch == 1) {
         if (!e->stem2_f) return fail(ASRB_E_WEIGHTS, "conv2.0.weight was not supplied: single-channel input unsupported");
@@ -293,7 +291,7 @@ int encoder_stem(asrb_encoder* e, const EncBuffers& w, const float* x_c1, int in
     }
     if (bf) {
         TcGemmArgs g{};
-        g.A = (const __nv_bfloat16*)w.a0; g.W = e->stem1_h; g.bias = e->stem1_b; g.out = X;
+        g.A = (const op16*)w.a0; g.W = e->stem1_h; g.bias = e->stem1_b; g.out = X;
         g.B = B; g.T = T; g.K = e->CP; g.N = D; g.taps = 3; g.epilogue = TC_BIAS_ACT; g.act = stem_act;
         return launch_gemm_tc(g, st);
     }
@@ -313,7 +311,7 @@ int encoder_body(asrb_encoder* e, const EncBuffers& w, const float* x_c1, int in
 int encoder_layers(asrb_encoder* e, const EncBuffers& w, int64_t B, int64_t T, void* out, int out_dtype, cudaStream_t st) {
     const int D = e->cfg.dims, L = e->cfg.layer;
     const bool bf = e->cfg.compute == ASRB_BF16;
-    const DType dt = bf ? DT_BF16 : DT_F32;
+    const DType dt = bf ? DT_OP16 : DT_F32;
     const int64_t rows = B * T;
 
     ASRB_TRY(launch_pos_table(w.pos, e->pos_scales, T, D, st));
@@ -324,26 +322,26 @@ int encoder_layers(asrb_encoder* e, const EncBuffers& w, int64_t B, int64_t T, v
         const LayerW& lw = e->layers[i];
         const bool last = i == L - 1;
         if (bf) {
-            ASRB_TRY(tc_gemm_ln((const __nv_bfloat16*)w.X, lw.wc_h, lw.bc, nullptr, lw.gamma, lw.beta, w.Y, w.H, B, T, D, D, 3, st));
+            ASRB_TRY(tc_gemm_ln((const op16*)w.X, lw.wc_h, lw.bc, nullptr, lw.gamma, lw.beta, w.Y, w.H, B, T, D, D, 3, st));
             // point1 + GLU + depthwise-15 (BatchNorm folded) + SiLU in one kernel: Y -> U
             TcGemmArgs g{};
-            g.A = (const __nv_bfloat16*)w.Y; g.W = lw.w1_h; g.bias = lw.b1_glu; g.out = w.U;
+            g.A = (const op16*)w.Y; g.W = lw.w1_h; g.bias = lw.b1_glu; g.out = w.U;
             g.B = B; g.T = T; g.K = D; g.N = 2 * D; g.taps = 1; g.epilogue = TC_GLU_DW; g.act = ACT_NONE;
             g.dw_w = lw.dw15; g.dw_b = lw.dw15_b; g.dw_kw = 15; g.dw_act = ACT_SILU;
             ASRB_TRY(launch_gemm_tc(g, st));
             TcGemmArgs h{};
-            h.A = (const __nv_bfloat16*)w.U; h.W = lw.w2_h; h.bias = lw.b2; h.res = (const __nv_bfloat16*)w.Y;
+            h.A = (const op16*)w.U; h.W = lw.w2_h; h.bias = lw.b2; h.res = (const op16*)w.Y;
             h.B = B; h.T = T; h.K = D; h.N = D; h.taps = 1; h.act = ACT_GELU;
             // point2 + residual + GELU + depthwise-3 + GELU (+ next block's GELU | + sinusoids): U, Y -> X
             const bool to_out = last && !e->cfg.enc && out_dtype == ASRB_BF16;
-            h.epilogue = TC_RES_ACT_DW; h.out = to_out ? out : w.X;
+            h.epilogue = TC_RES_ACT_DW; h.out = to_out ? out : w.X; h.out_bf16 = to_out;
             h.dw_w = lw.dw3; h.dw_b = lw.dw3_b; h.dw_kw = 3; h.dw_act = last ? ACT_GELU : ACT_GELU_GELU;
             h.pos = last ? w.pos : nullptr;
             h.out32 = (last && e->cfg.enc && tc_gemm_supported(D, D, TC_LN)) ? (float*)w.G : nullptr;
             ASRB_TRY(launch_gemm_tc(h, st));
             if (last && !e->cfg.enc && out_dtype != ASRB_BF16) {
                 ProfScope ps("convert", st, 0.0, 6.0 * rows * D);
-                convert_kernel<<<148 * 8, 256, 0, st>>>((const __nv_bfloat16*)w.X, (float*)out, rows * D);
+                convert_kernel<op16, float><<<148 * 8, 256, 0, st>>>((const op16*)w.X, (float*)out, rows * D);
                 ASRB_LAUNCH_CHECK();
             }
             continue;
@@ -355,13 +353,14 @@ int encoder_layers(asrb_encoder* e, const EncBuffers& w, int64_t B, int64_t T, v
             ASRB_TRY(launch_dwconv(w.G, DT_F32, lw.dw15, lw.dw15_b, w.U, DT_F32, B, T, D, 15, ACT_SILU, nullptr, false, st));
             ASRB_TRY(launch_gemm_simt(w.U, DT_F32, lw.w2_f, lw.b2, w.Y, w.H, DT_F32, B, T, D, D, 1, ACT_GELU, st));
         }
-        // depthwise k3 + GELU (+ the next block's leading GELU; + sinusoids after the last block)
-        void* dst = w.X; DType ddt = dt;
-        if (last && direct_out) { dst = out; ddt = out_dtype == ASRB_BF16 ? DT_BF16 : DT_F32; }
-        // with the TransformerEncoderLayer the residual streams stay fp32 (x32 = fp32 copy of the stack output)
-        float* x32 = (last && bf && e->cfg.enc && tc_gemm_supported(D, D, TC_LN)) ? (float*)w.G : nullptr;
-        ASRB_TRY(launch_dwconv(w.H, bf ? DT_F32 : dt, lw.dw3, lw.dw3_b, dst, ddt, B, T, D, 3, last ? ACT_GELU : ACT_GELU_GELU,
-                               last ? w.pos : nullptr, bf, st, x32));
+        // fp32 variant: depthwise k3 + GELU (+ the next block's leading GELU; + sinusoids after the last block)
+        const bool to_out = last && direct_out && out_dtype == ASRB_F32;
+        ASRB_TRY(launch_dwconv(w.H, DT_F32, lw.dw3, lw.dw3_b, to_out ? out : w.X, DT_F32, B, T, D, 3, last ? ACT_GELU : ACT_GELU_GELU,
+                               last ? w.pos : nullptr, false, st, nullptr));
+        if (last && direct_out && !to_out) {               // fp32 variant asked for bf16 hidden states
+            convert_kernel<float, __nv_bfloat16><<<148 * 8, 256, 0, st>>>((const float*)w.X, (__nv_bfloat16*)out, rows * D);
+            ASRB_LAUNCH_CHECK();
+        }
     }
     if (!e->cfg.enc) return ASRB_OK;
 
@@ -372,23 +371,23 @@ int encoder_layers(asrb_encoder* e, const EncBuffers& w, int64_t B, int64_t T, v
     void* fin = same ? out : w.U;
     if (bf) {
         TcGemmArgs q{};
-        q.A = (const __nv_bfloat16*)w.X; q.W = e->win_h; q.bias = e->bin; q.out = w.wide;
+        q.A = (const op16*)w.X; q.W = e->win_h; q.bias = e->bin; q.out = w.wide;
         q.B = B; q.T = T; q.K = D; q.N = 3 * D; q.taps = 1; q.epilogue = TC_BIAS_ACT; q.act = ACT_NONE;
         ASRB_TRY(launch_gemm_tc(q, st));
         if (attention_tc_supported(D, H)) ASRB_TRY(launch_attention_tc(w.wide, w.U, B, T, D, H, scale, st));
-        else ASRB_TRY(launch_attention_simt(w.wide, w.U, DT_BF16, B, T, D, H, scale, st));
+        else ASRB_TRY(launch_attention_simt(w.wide, w.U, DT_OP16, B, T, D, H, scale, st));
         const bool fused_ln = tc_gemm_supported(D, D, TC_LN);
         float* x32 = fused_ln ? (float*)w.G : nullptr;       // written by the last depthwise kernel
         float* y32 = fused_ln ? (float*)w.H : nullptr;
-        ASRB_TRY(tc_gemm_ln((const __nv_bfloat16*)w.U, e->wo_h, e->bo, (const __nv_bfloat16*)w.X, e->n1g, e->n1b, w.Y, w.wide, B, T, D, D, 1, st, x32, y32));
+        ASRB_TRY(tc_gemm_ln((const op16*)w.U, e->wo_h, e->bo, (const op16*)w.X, e->n1g, e->n1b, w.Y, w.wide, B, T, D, D, 1, st, x32, y32));
         TcGemmArgs f1{};
-        f1.A = (const __nv_bfloat16*)w.Y; f1.W = e->wf1_h; f1.bias = e->bf1; f1.out = w.ffn;
+        f1.A = (const op16*)w.Y; f1.W = e->wf1_h; f1.bias = e->bf1; f1.out = w.ffn;
         f1.B = B; f1.T = T; f1.K = D; f1.N = F; f1.taps = 1; f1.epilogue = TC_BIAS_ACT; f1.act = ACT_RELU;
         ASRB_TRY(launch_gemm_tc(f1, st));
-        ASRB_TRY(tc_gemm_ln((const __nv_bfloat16*)w.ffn, e->wf2_h, e->bf2, (const __nv_bfloat16*)w.Y, e->n2g, e->n2b, fin, w.wide, B, T, F, D, 1, st, y32, nullptr));
+        ASRB_TRY(tc_gemm_ln((const op16*)w.ffn, e->wf2_h, e->bf2, (const op16*)w.Y, e->n2g, e->n2b, fin, w.wide, B, T, F, D, 1, st, y32, nullptr, same ? 1 : 0));
         if (!same) {
             ProfScope ps("convert", st, 0.0, 6.0 * rows * D);
-            convert_kernel<<<148 * 8, 256, 0, st>>>((const __nv_bfloat16*)fin, (float*)out, rows * D);
+            convert_kernel<op16, float><<<148 * 8, 256, 0, st>>>((const op16*)fin, (float*)out, rows * D);
             ASRB_LAUNCH_CHECK();
         }
     } else {
@@ -399,7 +398,7 @@ int encoder_layers(asrb_encoder* e, const EncBuffers& w, int64_t B, int64_t T, v
         ASRB_TRY(launch_gemm_simt(w.Y, DT_F32, e->wf1_f, e->bf1, nullptr, w.ffn, DT_F32, B, T, D, F, 1, ACT_RELU, st));
         ASRB_TRY(launch_gemm_simt(w.ffn, DT_F32, e->wf2_f, e->bf2, w.Y, w.H, DT_F32, B, T, F, D, 1, ACT_NONE, st));
         ASRB_TRY(launch_layernorm(w.H, nullptr, e->n2g, e->n2b, fin, DT_F32, rows, D, 1e-5f, st));
-        if (!same) { convert_kernel<<<148 * 8, 256, 0, st>>>((const float*)fin, (__nv_bfloat16*)out, rows * D); ASRB_LAUNCH_CHECK(); }
+        if (!same) { convert_kernel<float, __nv_bfloat16><<<148 * 8, 256, 0, st>>>((const float*)fin, (__nv_bfloat16*)out, rows * D); ASRB_LAUNCH_CHECK(); }
     }
     return ASRB_OK;
 }
@@ -435,7 +434,7 @@ extern "C" int asrb_encoder_forward(asrb_encoder* e, const float* x, int64_t B, 
     if (!w.ok) return fail(ASRB_E_WORKSPACE, "asrb_encoder_forward: workspace carve failed");
     const bool bf = e->cfg.compute == ASRB_BF16;
     if (in_ch != 1)
-        ASRB_TRY(launch_to_channels_last(x, w.a0, bf ? DT_BF16 : DT_F32, B, in_ch, bf ? e->CP : in_ch, T,
+        ASRB_TRY(launch_to_channels_last(x, w.a0, bf ? DT_OP16 : DT_F32, B, in_ch, bf ? e->CP : in_ch, T,
                                          nullptr, nullptr, 0, 1, false, st));
     return encoder_body(e, w, x, in_ch, B, T, out, out_dtype, st);
 }
@@ -460,7 +459,7 @@ extern "C" int asrb_encoder_forward_streams(asrb_encoder* e, int32_t n_streams, 
     const size_t es = bf ? 2 : 4;
     for (int s = 0; s < n_streams; ++s) {                  // stems one by one (conv1 | conv2), into stream s's rows of X
         if (in_ch[s] != 1)
-            ASRB_TRY(launch_to_channels_last(x[s], w.a0, bf ? DT_BF16 : DT_F32, B, in_ch[s], bf ? e->CP : in_ch[s], T,
+            ASRB_TRY(launch_to_channels_last(x[s], w.a0, bf ? DT_OP16 : DT_F32, B, in_ch[s], bf ? e->CP : in_ch[s], T,
                                              nullptr, nullptr, 0, 1, false, st));
         ASRB_TRY(encoder_stem(e, w, x[s], in_ch[s], B, T, (char*)w.X + (size_t)s * B * T * e->cfg.dims * es, st));
     }
@@ -499,13 +498,13 @@ extern "C" int asrb_pcm_to_hidden(const asrb_logmel_plan* pl, asrb_encoder* e, c
     const bool bf = e->cfg.compute == ASRB_BF16;
     if (bf && !logmel_out) {
         // the front end writes the stem GEMM's operand itself (bf16 channels-last) and the floor runs in place
-        ASRB_TRY(logmel_pass1(pl, pcm, B, n_samples, pcm_stride, lengths, nullptr, keys, st, (__nv_bfloat16*)w.a0, e->CP));
-        ASRB_TRY(logmel_floor_cl(pl, (__nv_bfloat16*)w.a0, e->CP, keys, lengths, B, n_samples, st));
+        ASRB_TRY(logmel_pass1(pl, pcm, B, n_samples, pcm_stride, lengths, nullptr, keys, st, (op16*)w.a0, e->CP));
+        ASRB_TRY(logmel_floor_cl(pl, (op16*)w.a0, e->CP, keys, lengths, B, n_samples, st));
         return encoder_body(e, w, nullptr, pl->n_mels, B, T, out, out_dtype, st);
     }
     ASRB_TRY(logmel_pass1(pl, pcm, B, n_samples, pcm_stride, lengths, mel, keys, st));
     // the dynamic-range floor (essentials.py:489) is applied while changing layout for conv1
-    ASRB_TRY(launch_to_channels_last(mel, w.a0, bf ? DT_BF16 : DT_F32, B, pl->n_mels, bf ? e->CP : pl->n_mels, T,
+    ASRB_TRY(launch_to_channels_last(mel, w.a0, bf ? DT_OP16 : DT_F32, B, pl->n_mels, bf ? e->CP : pl->n_mels, T,
                                      keys, lengths, n_samples, pl->hop, logmel_out != nullptr, st));
     return encoder_body(e, w, nullptr, pl->n_mels, B, T, out, out_dtype, st);
 }

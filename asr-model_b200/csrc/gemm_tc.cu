@@ -2,15 +2,15 @@
 //
 //   out[b,t,:] = epilogue( sum_{tap,k} A[b, t+tap-taps/2, k] * W[n][tap*K + k] )
 //
-// A is channels-last bf16 [B][T][K]; a 3-D TMA map (K, T, B) with OOB zero fill supplies the
+// A is channels-last op16 (the 16-bit operand format, common.cuh) [B][T][K]; a 3-D TMA map (K, T, B) with OOB zero fill supplies the
 // conv halo (t = -1, t = T) and the ragged last tile of every utterance for free.  W is
-// bf16 [N][taps*K], K-major.  Accumulators live in TMEM (fp32).  Roles per CTA (1 CTA / SM):
+// op16 [N][taps*K], K-major.  Accumulators live in TMEM (fp32).  Roles per CTA (1 CTA / SM):
 //   warp 0      TMA producer   (A box 64x128, W box 64xBN, SWIZZLE_128B, 3-5 stage ring)
 //   warp 1      MMA issuer     (tcgen05.mma cta_group::1 kind::f16, M=128, N=BN)
 //               both run their loops convergently with one elected lane issuing, so stage, phase and
 //               descriptors stay in uniform registers and the UTCHMMAs of a k-block go out back to back
 //   warps 2..   epilogue       (BN/64 column groups x four TMEM lane quadrants; thread = row)
-// Epilogues (fp32 math, bf16 store through swizzled smem + TMA store, which also clips the
+// Epilogues (fp32 math, 16-bit store through swizzled smem + TMA store, which also clips the
 // rows past T):  bias+act | bias+residual+act | bias(+residual)+LayerNorm over the full row (N <= 512:
 // a CTA pair owns one 256-column half each and swaps row sums over DSMEM).  The two epilogues with a
 // fused depthwise convolution (TC_GLU_DW, TC_RES_ACT_DW) live in gemm_tct.cu (lanes = channels).
@@ -214,7 +214,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     if (p.out32 && row_ok) store_f32x32(p.out32 + grow * p.N + gbase + c, v);   // fp32 copy: the next residual stream
                     const int cb = (c - c_begin) & 32;                        // which half of the 64-column staging tile
                     if (cb == 0) { if (leader) tma_wait_read0(); epi_bar(bar_id, 128); }
-                    stage_store32(stg, r, cb, v);
+                    stage_store32(stg, r, cb, v, p.out_bf16 != 0);
                     if (cb == 32) {
                         fence_async_smem();
                         epi_bar(bar_id, 128);
@@ -243,7 +243,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         if (leader) { tma_store_3d(&map_out, stg_u32, gc + 32 * hh, t0, b); tma_commit(); }
                     } else {
                         if (hh == 0) { if (leader) tma_wait_read0(); epi_bar(bar_id, 128); }
-                        stage_store32(stg, r, 32 * hh, v);
+                        stage_store32(stg, r, 32 * hh, v, p.out_bf16 != 0);
                         if (hh == 1) {
                             fence_async_smem();
                             epi_bar(bar_id, 128);
@@ -351,7 +351,7 @@ int tc_prepare(const TcGemmArgs& a, CUtensorMap* ma, CUtensorMap* mw, CUtensorMa
     p.halo = halo; p.rows_out = rows_out;
     p.tiles_per_utt = (int)((a.T + rows_out - 1) / rows_out);
     p.m_tiles = (int)(a.B * p.tiles_per_utt);
-    p.n_chunks = a.N / bn; p.n_out = n_out; p.eps = a.eps; p.out_f32 = a.out_f32;
+    p.n_chunks = a.N / bn; p.n_out = n_out; p.eps = a.eps; p.out_f32 = a.out_f32; p.out_bf16 = a.out_bf16;
     p.cluster = (a.epilogue == TC_LN && bn == 256 && a.N == 512) ? 2 : 1;     // the 128 x 512 row block fills TMEM: split it over a CTA pair
     *bn_out = bn;
     return ASRB_OK;
@@ -407,7 +407,7 @@ extern "C" int asrb_test_gemm_tc(const void* a, const void* w, const float* bias
     if (epilogue < 0 || epilogue > 5 || (taps != 1 && taps != 3)) return fail(ASRB_E_ARG, "asrb_test_gemm_tc: bad epilogue/taps");
     ASRB_TRY(require_sm100());
     TcGemmArgs g{};
-    g.A = (const __nv_bfloat16*)a; g.W = (const __nv_bfloat16*)w; g.bias = bias; g.res = (const __nv_bfloat16*)res;
+    g.A = (const op16*)a; g.W = (const op16*)w; g.bias = bias; g.res = (const op16*)res;
     g.gamma = gamma; g.beta = beta; g.out = out;
     g.B = B; g.T = T; g.K = K; g.N = N; g.taps = taps; g.epilogue = epilogue; g.act = act; g.eps = 1e-5f;
     g.dw_w = dw_w; g.dw_b = dw_b; g.dw_kw = dw_kw; g.dw_act = dw_act; g.pos = pos;

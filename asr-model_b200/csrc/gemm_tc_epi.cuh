@@ -53,28 +53,36 @@ __device__ __forceinline__ void act_fast32(float (&v)[32], int act) {      // sw
         default: break;
     }
 }
-__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
-    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-    return *reinterpret_cast<uint32_t*>(&h);
-}
 
 struct TcParams {
-    const float* bias; const __nv_bfloat16* res; const float* res32; float* out32; const float* gamma; const float* beta;
-    int T, K, N, taps, act, tiles_per_utt, m_tiles, n_chunks, n_out, out_f32;
+    const float* bias; const op16* res; const float* res32; float* out32; const float* gamma; const float* beta;
+    int T, K, N, taps, act, tiles_per_utt, m_tiles, n_chunks, n_out, out_f32, out_bf16;
     int cluster;                 // TC_LN with N = 512: 2 CTAs own one 256-column half each and swap row sums over DSMEM
     float eps;
     int halo, rows_out;          // rows_out = 128 frames per tile, halo = 0 (kept for the tile arithmetic)
 };
 
-// 32 fp32 values of one row -> 32 bf16 into the swizzled staging tile (row r, columns cb..cb+31 of 64)
-__device__ __forceinline__ void stage_store32(unsigned char* staging, int r, int cb, const float (&v)[32]) {
+// 32 fp32 values of one row -> 32 16-bit values into the swizzled staging tile (row r, columns cb..cb+31 of 64);
+// as_bf16 (warp-uniform): this tile is the encoder's result, otherwise the next MMA's operand
+__device__ __forceinline__ void stage_store32(unsigned char* staging, int r, int cb, const float (&v)[32], bool as_bf16 = false) {
+    if (as_bf16) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int chunk = (cb >> 3) + i;                              // 16-byte chunk index 0..7 in the 128-B row
-        uint4 q;
-        q.x = pack_bf16(v[8 * i + 0], v[8 * i + 1]); q.y = pack_bf16(v[8 * i + 2], v[8 * i + 3]);
-        q.z = pack_bf16(v[8 * i + 4], v[8 * i + 5]); q.w = pack_bf16(v[8 * i + 6], v[8 * i + 7]);
-        *reinterpret_cast<uint4*>(staging + r * 128 + ((chunk ^ (r & 7)) << 4)) = q;
+        for (int i = 0; i < 4; ++i) {
+            const int chunk = (cb >> 3) + i;                          // 16-byte chunk index 0..7 in the 128-B row
+            uint4 q;
+            q.x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]); q.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
+            q.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]); q.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
+            *reinterpret_cast<uint4*>(staging + r * 128 + ((chunk ^ (r & 7)) << 4)) = q;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int chunk = (cb >> 3) + i;
+            uint4 q;
+            q.x = pack_op16x2(v[8 * i + 0], v[8 * i + 1]); q.y = pack_op16x2(v[8 * i + 2], v[8 * i + 3]);
+            q.z = pack_op16x2(v[8 * i + 4], v[8 * i + 5]); q.w = pack_op16x2(v[8 * i + 6], v[8 * i + 7]);
+            *reinterpret_cast<uint4*>(staging + r * 128 + ((chunk ^ (r & 7)) << 4)) = q;
+        }
     }
 }
 // 32 fp32 values of one row -> one 128-byte swizzled staging row (fp32 output tiles are 32 columns wide)
@@ -83,13 +91,13 @@ __device__ __forceinline__ void stage_store32_f32(unsigned char* staging, int r,
     for (int i = 0; i < 8; ++i)
         *reinterpret_cast<float4*>(staging + r * 128 + ((i ^ (r & 7)) << 4)) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
 }
-__device__ __forceinline__ void add_res32(float (&v)[32], const __nv_bfloat16* rp) {
+__device__ __forceinline__ void add_res32(float (&v)[32], const op16* rp) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const uint4 q = *reinterpret_cast<const uint4*>(rp + 8 * i);
-        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+        const uint32_t* h = reinterpret_cast<const uint32_t*>(&q);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { const float2 f = __bfloat1622float2(h[j]); v[8 * i + 2 * j] += f.x; v[8 * i + 2 * j + 1] += f.y; }
+        for (int j = 0; j < 4; ++j) { const float2 f = unpack_op16x2(h[j]); v[8 * i + 2 * j] += f.x; v[8 * i + 2 * j + 1] += f.y; }
     }
 }
 __device__ __forceinline__ void add_f32x32(float (&v)[32], const float* p) {     // plain (not read-only) loads

@@ -12,7 +12,7 @@
 //   TC_RES_ACT_DW  point2 (1x1) + bias + residual + GELU -> depthwise-3 -> GELU[∘GELU] (+ sinusoids)
 //                  model.py:116-118,145-147,160-161.  256 frames per tile (1 halo frame each side).  The
 //                  residual is added by the tensor core as two extra k-blocks  I[128x128] * Y^T  (exact:
-//                  bf16 x 1.0 into the fp32 accumulator), so the epilogue issues no residual loads.
+//                  operand x 1.0 into the fp32 accumulator), so the epilogue issues no residual loads.
 //   TC_GLU_DW      point1 (1x1, D -> 2D) + GLU -> depthwise-15 (eval BatchNorm folded) -> SiLU
 //                  model.py:111-115.  128 frames per tile (112 produced), value and gate halves of the
 //                  same 128 channels in two accumulators (two MMAs per k-step share the frame tile).
@@ -45,7 +45,7 @@ template <> struct TctCfg<TC_GLU_DW> {
 };
 
 struct TctParams {
-    const float* bias; const float* dw_w; const float* dw_b; const float* pos; float* out32; __nv_bfloat16* out;
+    const float* bias; const float* dw_w; const float* dw_b; const float* pos; float* out32; uint16_t* out;
     int T, K, n_out, tiles_per_utt, m_tiles, n_ct;
 };
 
@@ -92,7 +92,11 @@ __device__ __forceinline__ void tmem_ld2_nw(uint32_t taddr, float* v) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-__device__ __forceinline__ void st_bf16(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+// one 16-bit store: OBF = the encoder's result (bf16), otherwise the next MMA's operand (op16)
+template <bool OBF> __device__ __forceinline__ void st16(uint16_t* p, float v) {
+    if (OBF) *reinterpret_cast<__nv_bfloat16*>(p) = __float2bfloat16_rn(v);
+    else *reinterpret_cast<op16*>(p) = to_op16(v);
+}
 
 // Taps and bias of the depthwise-3, halved (the activation that follows takes x / 2)
 struct Dw3 { float w0, w1, w2, b; };
@@ -104,7 +108,7 @@ struct Dw3 { float w0, w1, w2, b; };
 //                 every output is this group's except possibly the first two (skip2);
 //   MASK = true : general warp-uniform predicates (tile touching the end of the utterance).
 // NO = n_out as a compile-time constant (store offsets become immediates) or 0. ----
-template <bool MASK, int NO, int ACT2>
+template <bool MASK, int NO, int ACT2, bool OBF>
 __device__ __forceinline__ void dw3_chunk(float (&v)[32], float& pa, float& pb, float hbias, const Dw3& k, const TctParams& p,
                                           int tS, int t_lo, int t_hi, bool skip2, bool zero_first, int64_t row0 /* b*T */, int c) {
     const int ld = NO ? NO : p.n_out;
@@ -139,9 +143,9 @@ __device__ __forceinline__ void dw3_chunk(float (&v)[32], float& pa, float& pb, 
 #pragma unroll
             for (int jj = 0; jj < 16; ++jj) if (live(jj)) p.out32[eh + (int64_t)jj * ld] = o[jj];
         }
-        __nv_bfloat16* op = p.out + eh;
+        uint16_t* op = p.out + eh;
 #pragma unroll
-        for (int jj = 0; jj < 16; ++jj) if (live(jj)) st_bf16(op + (int64_t)jj * ld, o[jj]);
+        for (int jj = 0; jj < 16; ++jj) if (live(jj)) st16<OBF>(op + (int64_t)jj * ld, o[jj]);
     }
 }
 
@@ -150,7 +154,7 @@ __device__ __forceinline__ void dw3_chunk(float (&v)[32], float& pa, float& pb, 
 // outside [0, T) (conv zero padding; outputs past T are dropped).  4 outputs x 2 partial sums = 8 independent
 // FFMA chains at a time. ----
 template <bool MASK, int NO, int ACT2>
-__device__ __forceinline__ void dw15_emit(float (&h)[44], const float (&k)[16], __nv_bfloat16* op, int ldr, int tw, int T) {
+__device__ __forceinline__ void dw15_emit(float (&h)[44], const float (&k)[16], uint16_t* op, int ldr, int tw, int T) {
     const int ld = NO ? NO : ldr;
     if (MASK) {
 #pragma unroll
@@ -172,14 +176,14 @@ __device__ __forceinline__ void dw15_emit(float (&h)[44], const float (&k)[16], 
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const float o = act2_h<ACT2>(s0[q] + s1[q]);
-            if (!MASK || tw + 8 + j0 + q < T) st_bf16(op + (int64_t)(j0 + q) * ld, o);
+            if (!MASK || tw + 8 + j0 + q < T) st16<false>(op + (int64_t)(j0 + q) * ld, o);
         }
     }
 }
 
 }  // namespace
 
-template <int EPI, int NO, int ACT2>
+template <int EPI, int NO, int ACT2, bool OBF>
 __global__ void __launch_bounds__(TCT_THREADS, 1)
 gemm_tct_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x,
                 const __grid_constant__ CUtensorMap map_i, const __grid_constant__ CUtensorMap map_r, const TctParams p) {
@@ -347,9 +351,9 @@ gemm_tct_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
                     if (ch == 1) { tc_fence_before(); mbar_arrive(tempty_bar(a)); }   // last TMEM read of this unit
                     if (tS - 1 >= p.T) continue;            // nothing left to emit (warp-uniform)
                     if (tS + 31 < p.T)
-                        dw3_chunk<false, NO, ACT2>(v, pa, pb, hb0, kk, p, tS, t_lo, t_hi, g == 0 && ch == 0, tS < 0, row0, c);
+                        dw3_chunk<false, NO, ACT2, OBF>(v, pa, pb, hb0, kk, p, tS, t_lo, t_hi, g == 0 && ch == 0, tS < 0, row0, c);
                     else
-                        dw3_chunk<true, NO, ACT2>(v, pa, pb, hb0, kk, p, tS, t_lo, t_hi, false, false, row0, c);
+                        dw3_chunk<true, NO, ACT2, OBF>(v, pa, pb, hb0, kk, p, tS, t_lo, t_hi, false, false, row0, c);
                 }
             } else {
                 // ---- GLU -> depthwise-15 -> act2.  Two TEAMS of 8 warps alternate over the units (team = accumulator
@@ -385,7 +389,7 @@ gemm_tct_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
 #pragma unroll
                         for (int i = 0; i < 12; ++i) h[32 + i] = glu(h[32 + i], gt[i]);
                     }
-                    __nv_bfloat16* op = p.out + (row0 + tw + 8) * ld + c;
+                    uint16_t* op = p.out + (row0 + tw + 8) * ld + c;
                     if (tw >= 0 && tw + 43 < p.T) dw15_emit<false, NO, ACT2>(h, k, op, ld, tw, p.T);
                     else dw15_emit<true, NO, ACT2>(h, k, op, ld, tw, p.T);
                 }
@@ -404,7 +408,7 @@ gemm_tct_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
                     mbar_arrive(tempty_bar(a));             // this warp's last TMEM read of the unit
 #pragma unroll
                     for (int i = 0; i < 28; ++i) h[16 + i] = glu(h[16 + i], gt[i]);
-                    __nv_bfloat16* op = p.out + (row0 + tw + 8) * ld + c;
+                    uint16_t* op = p.out + (row0 + tw + 8) * ld + c;
                     if (tw >= 0 && tw + 43 < p.T) dw15_emit<false, NO, ACT2>(h, k, op, ld, tw, p.T);
                     else dw15_emit<true, NO, ACT2>(h, k, op, ld, tw, p.T);
                 }
@@ -456,19 +460,19 @@ int make_frames_map(CUtensorMap* m, const void* base, int64_t B, int64_t T, int 
 
 // 128 x 128 bf16 identity: the A operand of the residual k-blocks.  One per device, created on first use
 // (asrb_encoder_create touches it, so a captured forward never allocates).
-const __nv_bfloat16* tct_identity() {
+const op16* tct_identity() {
     static std::mutex mu;
-    static __nv_bfloat16* table[64] = {};
+    static op16* table[64] = {};
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
     std::lock_guard<std::mutex> lk(mu);
     if (!table[dev]) {
-        std::vector<__nv_bfloat16> h(128 * 128, __float2bfloat16_rn(0.f));
-        for (int i = 0; i < 128; ++i) h[i * 128 + i] = __float2bfloat16_rn(1.f);
+        std::vector<op16> h(128 * 128, host_to_op16(0.f));
+        for (int i = 0; i < 128; ++i) h[i * 128 + i] = host_to_op16(1.f);
         void* d = nullptr;
-        if (cudaMalloc(&d, h.size() * sizeof(__nv_bfloat16)) != cudaSuccess) return nullptr;
-        if (cudaMemcpy(d, h.data(), h.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice) != cudaSuccess) { cudaFree(d); return nullptr; }
-        table[dev] = (__nv_bfloat16*)d;
+        if (cudaMalloc(&d, h.size() * sizeof(op16)) != cudaSuccess) return nullptr;
+        if (cudaMemcpy(d, h.data(), h.size() * sizeof(op16), cudaMemcpyHostToDevice) != cudaSuccess) { cudaFree(d); return nullptr; }
+        table[dev] = (op16*)d;
     }
     return table[dev];
 }
@@ -477,12 +481,12 @@ bool tct_supported(const TcGemmArgs& a) {
     if (a.taps != 1 || a.K % 64 != 0 || a.out_f32 || !a.dw_w || !a.dw_b) return false;
     if (a.epilogue == TC_RES_ACT_DW)
         return a.N % 128 == 0 && a.dw_kw == 3 && a.res != nullptr && a.act == ACT_GELU &&
-               (a.dw_act == ACT_GELU || a.dw_act == ACT_GELU_GELU);
-    if (a.epilogue == TC_GLU_DW) return a.N % 256 == 0 && a.dw_kw == 15 && !a.pos && !a.out32 && a.dw_act == ACT_SILU;
+               (a.dw_act == ACT_GELU || (a.dw_act == ACT_GELU_GELU && !a.out_bf16));
+    if (a.epilogue == TC_GLU_DW) return a.N % 256 == 0 && a.dw_kw == 15 && !a.pos && !a.out32 && !a.out_bf16 && a.dw_act == ACT_SILU;
     return false;
 }
 
-template <int EPI, int NO, int ACT2>
+template <int EPI, int NO, int ACT2, bool OBF>
 static int launch_tct(const TcGemmArgs& a, cudaStream_t st) {
     using C = TctCfg<EPI>;
     constexpr bool RES = EPI == TC_RES_ACT_DW;
@@ -491,19 +495,19 @@ static int launch_tct(const TcGemmArgs& a, cudaStream_t st) {
     ASRB_TRY(make_mat_map(&mw, a.W, a.N, a.K, C::A_ROWS));
     ASRB_TRY(make_frames_map(&mx, a.A, a.B, a.T, a.K, C::NF));
     if (RES) {
-        const __nv_bfloat16* ident = tct_identity();
+        const op16* ident = tct_identity();
         if (!ident) return fail(ASRB_E_CUDA, "tcgen05 GEMM: identity operand unavailable");
         ASRB_TRY(make_mat_map(&mi, ident, 128, 128, 128));
         ASRB_TRY(make_frames_map(&mr, a.res, a.B, a.T, n_out, C::NF));
     } else { mi = mw; mr = mx; }
     TctParams p{};
-    p.bias = a.bias; p.dw_w = a.dw_w; p.dw_b = a.dw_b; p.pos = a.pos; p.out32 = a.out32; p.out = (__nv_bfloat16*)a.out;
+    p.bias = a.bias; p.dw_w = a.dw_w; p.dw_b = a.dw_b; p.pos = a.pos; p.out32 = a.out32; p.out = (uint16_t*)a.out;
     p.T = (int)a.T; p.K = a.K; p.n_out = n_out;
     p.tiles_per_utt = (int)((a.T + C::ROWS_OUT - 1) / C::ROWS_OUT);
     p.m_tiles = (int)(a.B * p.tiles_per_utt);
     p.n_ct = n_out / 128;
     const int units = p.m_tiles * p.n_ct;
-    auto kern = gemm_tct_kernel<EPI, NO, ACT2>;
+    auto kern = gemm_tct_kernel<EPI, NO, ACT2, OBF>;
     ASRB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TCT_SMEM));
     const int grid = units < sm_count() ? units : sm_count();
     kern<<<grid, TCT_THREADS, TCT_SMEM, st>>>(mw, mx, mi, mr, p);
@@ -513,11 +517,13 @@ static int launch_tct(const TcGemmArgs& a, cudaStream_t st) {
 
 int launch_gemm_tct(const TcGemmArgs& a, cudaStream_t st) {
     // n_out as a compile-time constant for the encoder widths of BASELINE.json (512, 1024); generic otherwise
-#define ASRB_TCT(EPI_, ACT_, no) \
-    ((no) == 512 ? launch_tct<EPI_, 512, ACT_>(a, st) : (no) == 1024 ? launch_tct<EPI_, 1024, ACT_>(a, st) : launch_tct<EPI_, 0, ACT_>(a, st))
-    if (a.epilogue == TC_RES_ACT_DW)
-        return a.dw_act == ACT_GELU_GELU ? ASRB_TCT(TC_RES_ACT_DW, ACT_GELU_GELU, a.N) : ASRB_TCT(TC_RES_ACT_DW, ACT_GELU, a.N);
-    return ASRB_TCT(TC_GLU_DW, ACT_SILU, a.N / 2);
+#define ASRB_TCT(EPI_, ACT_, OBF_, no) \
+    ((no) == 512 ? launch_tct<EPI_, 512, ACT_, OBF_>(a, st) : (no) == 1024 ? launch_tct<EPI_, 1024, ACT_, OBF_>(a, st) : launch_tct<EPI_, 0, ACT_, OBF_>(a, st))
+    if (a.epilogue == TC_RES_ACT_DW) {
+        if (a.dw_act == ACT_GELU_GELU) return ASRB_TCT(TC_RES_ACT_DW, ACT_GELU_GELU, false, a.N);     // feeds the next block's k3 conv
+        return a.out_bf16 ? ASRB_TCT(TC_RES_ACT_DW, ACT_GELU, true, a.N) : ASRB_TCT(TC_RES_ACT_DW, ACT_GELU, false, a.N);
+    }
+    return ASRB_TCT(TC_GLU_DW, ACT_SILU, false, a.N / 2);
 #undef ASRB_TCT
 }
 

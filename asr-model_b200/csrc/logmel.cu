@@ -29,7 +29,7 @@ struct LogmelParams {
     const int* mel_cnt;        // [M] taps (0 for an all-zero filter)
     const float* mel_w;        // [M][kmax]
     float* out;                // [B][M][T] fp32 (reference layout), or NULL with out_cl set
-    __nv_bfloat16* out_cl;     // fused path: [B][T][CP] bf16 channels-last, channels >= M zero (the stem GEMM's operand)
+    op16* out_cl;              // fused path: [B][T][CP] op16 channels-last, channels >= M zero (the stem GEMM's operand)
     int CP;
     uint32_t* keys;            // [B]
 };
@@ -74,9 +74,9 @@ logmel_kernel(const LogmelParams p, int tiles_per_utt, int total_tiles) {
     float*  s_melw = reinterpret_cast<float*>(s_y + C::GROUPS * C::YSTRIDE);   // [M][kmax]
     int*    s_lo  = reinterpret_cast<int*>(s_melw + p.M * p.kmax);      // [M]
     int*    s_cnt = s_lo + p.M;                                         // [M]
-    // fused path: the tile's [FB][CP] bf16 output is transposed through shared memory (pitch CP + 2 halves:
+    // fused path: the tile's [FB][CP] 16-bit output is transposed through shared memory (pitch CP + 2 halves:
     // frame-per-lane writes and row reads are both conflict free)
-    __nv_bfloat16* s_cl = reinterpret_cast<__nv_bfloat16*>(s_cnt + p.M + (p.M & 1));
+    op16* s_cl = reinterpret_cast<op16*>(s_cnt + p.M + (p.M & 1));
     const int clp = p.CP + 2;
     __shared__ float s_red[32];
 
@@ -85,7 +85,7 @@ logmel_kernel(const LogmelParams p, int tiles_per_utt, int total_tiles) {
 
     auto prefetch = [&](int tile, float* dstbuf) {       // async copy of one tile's PCM span
         const int b = tile / tiles_per_utt, t0 = (tile - b * tiles_per_utt) * FB;
-        const int64_t len = p.lengths ? (int64_t)p.lengths[b] : p.n_samples;
+        const int64_t len = clamp_len(p.lengths, b, p.n_samples);
         const float* src = p.pcm + (int64_t)b * p.stride;
         const int64_t s0 = (int64_t)t0 * p.hop - NFFT / 2;
         const uint32_t d0 = (uint32_t)__cvta_generic_to_shared(dstbuf);
@@ -114,7 +114,7 @@ logmel_kernel(const LogmelParams p, int tiles_per_utt, int total_tiles) {
     for (int i = tid; i < R * R; i += C::THREADS) s_tw[i] = p.twiddle[i];
     for (int i = tid; i < p.M * p.kmax; i += C::THREADS) s_melw[i] = p.mel_w[i];
     for (int i = tid; i < p.M; i += C::THREADS) { s_lo[i] = p.mel_lo[i]; s_cnt[i] = p.mel_cnt[i]; }
-    if (p.out_cl) for (int i = tid; i < FB * clp; i += C::THREADS) s_cl[i] = __float2bfloat16_rn(0.f);   // channels >= M stay 0
+    if (p.out_cl) for (int i = tid; i < FB * clp; i += C::THREADS) s_cl[i] = to_op16(0.f);   // channels >= M stay 0
 
     const int g = tid / R, j = tid - g * R;
     float2* yg = s_y + g * C::YSTRIDE;
@@ -131,8 +131,8 @@ logmel_kernel(const LogmelParams p, int tiles_per_utt, int total_tiles) {
         __syncthreads();                                    // this tile's PCM (and the constants) are visible
 
         const int b = tile / tiles_per_utt, t0 = (tile - b * tiles_per_utt) * FB;
-        const int64_t len = p.lengths ? (int64_t)p.lengths[b] : p.n_samples;
-        const int Tb = 1 + (int)(len / p.hop);              // valid frames of this utterance
+        const int64_t len = clamp_len(p.lengths, b, p.n_samples);
+        const int Tb = 1 + (int)(len / p.hop);              // valid frames of this utterance (<= T: len <= n_samples)
 
         // ---- round 1: R-point DFT over n1 of z[R n1 + j], twiddle W_N^(j k1), transpose ----
         {
@@ -218,7 +218,7 @@ logmel_kernel(const LogmelParams p, int tiles_per_utt, int total_tiles) {
                 if (t < p.T) {
                     float sv = 0.f;                                         // DataCollator pad value
                     if (t < Tb) { vmax = fmaxf(vmax, lg); sv = (lg + 4.0f) / 4.0f; }   // essentials.py:490
-                    if (p.out_cl) s_cl[fr * clp + m] = __float2bfloat16_rn(sv);
+                    if (p.out_cl) s_cl[fr * clp + m] = to_op16(sv);
                     else p.out[((int64_t)b * p.M + m) * p.T + t] = sv;
                 }
             }
@@ -226,7 +226,7 @@ logmel_kernel(const LogmelParams p, int tiles_per_utt, int total_tiles) {
         vmax = warp_max(vmax);
         if (lane == 0) s_red[warp] = vmax;
         __syncthreads();                                    // also: s_pow / s_pcm are free for the next tile
-        if (p.out_cl) {                                     // rows of CP bf16, two per 32-bit word: coalesced
+        if (p.out_cl) {                                     // rows of CP 16-bit values, two per 32-bit word: coalesced
             const int wpr = p.CP >> 1;
             uint32_t* dst = reinterpret_cast<uint32_t*>(p.out_cl + ((int64_t)b * p.T + t0) * p.CP);
             for (int i = tid; i < FB * wpr; i += C::THREADS) {
@@ -247,7 +247,7 @@ logmel_kernel(const LogmelParams p, int tiles_per_utt, int total_tiles) {
 __global__ void logmel_floor_kernel(float* out, const uint32_t* keys, const int32_t* lengths,
                                     int64_t n_samples, int hop, int M, int T) {
     const int b = blockIdx.y;
-    const int64_t len = lengths ? (int64_t)lengths[b] : n_samples;
+    const int64_t len = clamp_len(lengths, b, n_samples);
     const int Tb = 1 + (int)(len / hop);
     const float floor_s = ((key2f(keys[b]) - 8.0f) + 4.0f) / 4.0f;
     float* o = out + (int64_t)b * M * T;
@@ -262,32 +262,31 @@ __global__ void logmel_floor_kernel(float* out, const uint32_t* keys, const int3
     }
 }
 
-// The same floor on the fused path's bf16 channels-last tensor, in place: rounding is monotone, so
-// max(bf16(x), bf16(floor)) == bf16(max(x, floor)) bit for bit.  One thread per (frame, 8 channels).
-__global__ void logmel_floor_cl_kernel(__nv_bfloat16* a, const uint32_t* keys, const int32_t* lengths,
+// The same floor on the fused path's 16-bit channels-last tensor, in place: rounding is monotone, so
+// max(rn(x), rn(floor)) == rn(max(x, floor)) bit for bit.  One thread per (frame, 8 channels).
+__global__ void logmel_floor_cl_kernel(op16* a, const uint32_t* keys, const int32_t* lengths,
                                        int64_t n_samples, int hop, int M, int CP, int T) {
     const int b = blockIdx.y;
-    const int64_t len = lengths ? (int64_t)lengths[b] : n_samples;
-    const int Tb = 1 + (int)(len / hop);
-    const __nv_bfloat16 fl = __float2bfloat16_rn(((key2f(keys[b]) - 8.0f) + 4.0f) / 4.0f);
-    const __nv_bfloat162 fl2 = __halves2bfloat162(fl, fl);
+    const int64_t len = clamp_len(lengths, b, n_samples);
+    const int Tb = min(1 + (int)(len / hop), T);
+    const float fls = ((key2f(keys[b]) - 8.0f) + 4.0f) / 4.0f;
+    const float fl = unpack_op16x2(pack_op16x2(fls, fls)).x;           // the floor, rounded like the values were
     const int cpr = (M + 7) >> 3;                          // 16-byte chunks per row that hold real channels
     const int64_t total = (int64_t)Tb * cpr;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int t = (int)(i / cpr), c8 = (int)(i - (int64_t)t * cpr);
         uint4* ptr = reinterpret_cast<uint4*>(a + ((int64_t)b * T + t) * CP + c8 * 8);
         uint4 q = *ptr;
-        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&q);
+        uint32_t* h = reinterpret_cast<uint32_t*>(&q);
         bool changed = false;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            __nv_bfloat162 v = __hmax2(h[j], fl2);
-            if (c8 * 8 + 2 * j + 1 >= M) {                 // tail chunk: padded channels stay 0
-                if (c8 * 8 + 2 * j >= M) v = h[j];
-                else v = __halves2bfloat162(__low2bfloat16(v), __high2bfloat16(h[j]));
-            }
-            changed |= (*reinterpret_cast<uint32_t*>(&v) != *reinterpret_cast<uint32_t*>(&h[j]));
-            h[j] = v;
+            float2 v = unpack_op16x2(h[j]);
+            if (c8 * 8 + 2 * j < M) v.x = fmaxf(v.x, fl);                  // padded channels stay 0
+            if (c8 * 8 + 2 * j + 1 < M) v.y = fmaxf(v.y, fl);
+            const uint32_t u = pack_op16x2(v.x, v.y);
+            changed |= u != h[j];
+            h[j] = u;
         }
         if (changed) *ptr = q;
     }
@@ -369,7 +368,7 @@ static int launch_logmel(const asrb_logmel_plan* pl, LogmelParams p, int64_t bat
     const int span = (FB - 1) * pl->hop + NFFT;
     size_t smem = sizeof(float) * (2 * ((span + 3) & ~3) + NFFT) + sizeof(float2) * (R * R + C::GROUPS * C::YSTRIDE) +
                   sizeof(float) * (size_t)pl->n_mels * pl->kmax + sizeof(int) * (2 * pl->n_mels + 1) +
-                  (p.out_cl ? sizeof(__nv_bfloat16) * FB * (p.CP + 2) : 0);
+                  (p.out_cl ? sizeof(op16) * FB * (p.CP + 2) : 0);
     if (smem > 227 * 1024) return fail(ASRB_E_ARG, "asrb_logmel_f32: hop/n_mels need %zu B of shared memory", smem);
     auto kern = logmel_kernel<NFFT, R, FB>;
     ASRB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -389,7 +388,7 @@ static int launch_logmel(const asrb_logmel_plan* pl, LogmelParams p, int64_t bat
 // Shared by asrb_logmel_f32 and the fused pcm->hidden path: pass 1 only (values + keys).
 int logmel_pass1(const asrb_logmel_plan* pl, const float* pcm, int64_t batch, int64_t n_samples,
                  int64_t stride, const int32_t* lengths, float* out, uint32_t* keys, cudaStream_t st,
-                 __nv_bfloat16* out_cl, int CP) {
+                 op16* out_cl, int CP) {
     LogmelParams p;
     p.out_cl = out_cl; p.CP = CP;
     if (out_cl && (CP < pl->n_mels || (CP & 7))) return fail(ASRB_E_ARG, "log-mel: channels-last pitch %d for %d mels", CP, pl->n_mels);
@@ -406,7 +405,7 @@ int logmel_pass1(const asrb_logmel_plan* pl, const float* pcm, int64_t batch, in
 }
 
 // Floor of the fused path (after logmel_pass1 with out_cl).
-int logmel_floor_cl(const asrb_logmel_plan* pl, __nv_bfloat16* a, int CP, const uint32_t* keys, const int32_t* lengths,
+int logmel_floor_cl(const asrb_logmel_plan* pl, op16* a, int CP, const uint32_t* keys, const int32_t* lengths,
                     int64_t batch, int64_t n_samples, cudaStream_t st) {
     const int T = (int)(1 + n_samples / pl->hop);
     const int64_t per = (int64_t)T * ((pl->n_mels + 7) / 8);

@@ -11,10 +11,10 @@ namespace asrb {
 // Pass 1 of the front end: out = (log10(max(mel,1e-10)) + 4) / 4 without the dynamic-range
 // floor, keys[b] = order-preserving image of max_t,m log10(mel).  The floor is applied by
 // logmel_floor_kernel (asrb_logmel_f32) or on the fly by launch_to_channels_last.
-// With out_cl the values go out as bf16 channels-last [B][T][CP] (channels >= n_mels zero) instead of `out`.
+// With out_cl the values go out as op16 (16-bit operand format) channels-last [B][T][CP] (channels >= n_mels zero) instead of `out`.
 int logmel_pass1(const asrb_logmel_plan* pl, const float* pcm, int64_t batch, int64_t n_samples,
                  int64_t stride, const int32_t* lengths, float* out, uint32_t* keys, cudaStream_t st,
-                 __nv_bfloat16* out_cl = nullptr, int CP = 0);
-int logmel_floor_cl(const asrb_logmel_plan* pl, __nv_bfloat16* a, int CP, const uint32_t* keys, const int32_t* lengths,
+                 op16* out_cl = nullptr, int CP = 0);
+int logmel_floor_cl(const asrb_logmel_plan* pl, op16* a, int CP, const uint32_t* keys, const int32_t* lengths,
                     int64_t batch, int64_t n_samples, cudaStream_t st);
 }

@@ -121,9 +121,10 @@ __device__ __forceinline__ void epi_bar(int id, int threads) {
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
     return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
-// kind::f16 instruction descriptor: D fp32, A/B bf16, both K-major, M=128, N=BN (cute::UMMA::InstrDescriptor).
+// kind::f16 instruction descriptor: D fp32 (bits 4-5 = 1), A / B format (bits 7-9 / 10-12: 0 = fp16, 1 = bf16) = op16,
+// both K-major, M=128, N=BN (cute::UMMA::InstrDescriptor).
 __host__ __device__ constexpr uint32_t make_idesc(int bn) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    return (1u << 4) | (ASRB_OP16_IS_F16 ? 0u : ((1u << 7) | (1u << 10))) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 
 
@@ -169,7 +170,7 @@ inline EncodeTiledFn encode_fn() {
     return fn;
 }
 
-// [B][T][C] bf16 activations: dims (C, T, B), box 64 x 128 x 1, 128-byte swizzle, OOB -> 0
+// [B][T][C] 16-bit activations (op16 or bf16: the map only moves bits): dims (C, T, B), box 64 x 128 x 1, 128-byte swizzle, OOB -> 0
 inline int make_act_map(CUtensorMap* m, const void* base, int64_t B, int64_t T, int C, int box_rows = BM) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return fail(ASRB_E_CUDA, "cuTensorMapEncodeTiled entry point unavailable");

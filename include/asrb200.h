@@ -39,8 +39,14 @@ extern "C" {
 
 #define ASRB_F32   0
 #define ASRB_BF16  1
+#define ASRB_F16   2
 
 int         asrb_version(void);
+/* Storage format of the tensor-core variant's MMA operands (activations between kernels and packed weights):
+ * ASRB_F16 (IEEE fp16, the shipped build: same width and tensor throughput as bf16 with three more mantissa bits, which
+ * is what it takes to meet allclose(atol 2e-2, rtol 1e-2) against the fp32 reference -- DESIGN.md section 5) or
+ * ASRB_BF16 (a build with -DASRB_OPERAND_BF16).  Hidden states are returned as bf16 either way. */
+int         asrb_operand_format(void);
 const char* asrb_last_error(void);
 /* ASRB_OK iff `device` (ordinal) is a compute-capability 10.x GPU. */
 int         asrb_device_check(int device);
@@ -108,7 +114,9 @@ typedef struct asrb_encoder_config {
     int32_t layer;       /* number of conv blocks                                      */
     int32_t enc;         /* 1 = TransformerEncoderLayer present (model.py:138)         */
     int32_t ffn;         /* its feed-forward width (2048 in the reference)             */
-    int32_t compute;     /* ASRB_BF16: tcgen05 bf16 operands, fp32 accumulate;         */
+    int32_t compute;     /* ASRB_BF16: tcgen05 tensor-core variant -- 16-bit MMA       */
+                         /*   operands (asrb_operand_format()), fp32 accumulate, bf16  */
+                         /*   hidden states;                                           */
                          /* ASRB_F32 : fp32 FFMA everywhere (the 1e-4 variant)         */
     int32_t reserved;
 } asrb_encoder_config;
@@ -181,7 +189,8 @@ int asrb_profile_get(int index, const char** tag, float* ms, double* flops, doub
  * ---------------------------------------------------------------------------------- */
 /* The tcgen05/TMEM/TMA implicit-GEMM in isolation:
  *   out[b,t,:] = epilogue( sum_{tap,k} a[b, t+tap-taps/2, k] * w[n][tap*K + k] + bias[n] )
- * a [B][T][K] bf16, w [N][taps*K] bf16, out [B][T][N or N/2] bf16, res (or NULL) like out.
+ * a [B][T][K], w [N][taps*K], out [B][T][N or N/2], res (or NULL) like out: all in the 16-bit operand format
+ * (asrb_operand_format()).
  * epilogue: 0 bias+act | (1 reserved) |
  *           2 bias+res+act | 3 bias(+res)+LayerNorm(gamma, beta, eps=1e-5) |
  *           4 GLU (w rows interleaved [128 value | 128 gate] per 256) -> depthwise(dw_w [kw][N/2], dw_b)
@@ -196,8 +205,8 @@ int asrb_test_gemm_tc(const void* a, const void* w, const float* bias, const voi
                       const float* dw_w, const float* dw_b, int dw_kw, int dw_act, const float* pos,
                       void* stream);
 
-/* The tcgen05 flash-style attention in isolation: qkv [B][T][3D] bf16 (q | k | v, heads contiguous
- * inside each) -> out [B][T][D] bf16 = softmax(q k^T / sqrt(D/H)) v per head, no mask (model.py:163).
+/* The tcgen05 flash-style attention in isolation: qkv [B][T][3D] (q | k | v, heads contiguous inside each) ->
+ * out [B][T][D] = softmax(q k^T / sqrt(D/H)) v per head, no mask (model.py:163); both in the 16-bit operand format.
  * D/H must be 64 or 128. */
 int asrb_test_attention_tc(const void* qkv, void* out, int64_t B, int64_t T, int D, int H, void* stream);
 

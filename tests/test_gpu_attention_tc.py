@@ -1,5 +1,5 @@
 """The tcgen05 flash-style attention kernel in isolation (asrb_test_attention_tc) against a plain
-PyTorch fp32 softmax attention on the same bf16-rounded q, k, v."""
+PyTorch fp32 softmax attention on the same 16-bit-rounded q, k, v (the library's operand format)."""
 import math
 
 import pytest
@@ -22,9 +22,10 @@ CASES = [  # B, T, D, H
 def test_attention_tc_matches_torch(built_lib, B, T, D, H):
     lib = built_lib.load()
     g = torch.Generator(device="cuda").manual_seed(B * 7 + T + D + H)
-    qkv = (torch.randn(B, T, 3 * D, device="cuda", generator=g) * 1.5).bfloat16()
+    op = built_lib.operand_dtype()
+    qkv = (torch.randn(B, T, 3 * D, device="cuda", generator=g) * 1.5).to(op)
     qkv[..., :D] *= 2.0                                   # sharper softmax: the running max really moves
-    out = torch.full((B, T, D), float("nan"), device="cuda", dtype=torch.bfloat16)
+    out = torch.full((B, T, D), float("nan"), device="cuda", dtype=op)
     built_lib.check(lib.asrb_test_attention_tc(qkv.data_ptr(), out.data_ptr(), B, T, D, H, None), "asrb_test_attention_tc")
     torch.cuda.synchronize()
     hd = D // H
@@ -34,5 +35,6 @@ def test_attention_tc_matches_torch(built_lib, B, T, D, H):
     assert not torch.isnan(out.float()).any(), "rows were left unwritten"
     err = (out.float() - ref).abs()
     print(f"attention_tc B={B} T={T} D={D} H={H}: max {float(err.max()):.4f} mean {float(err.mean()):.5f} refmax {float(ref.abs().max()):.2f}")
-    assert bool((err <= 2e-2 + 2e-2 * ref.abs()).all()), float(err.max())     # P and O are bf16
-    assert float(err.mean()) < 3e-3
+    f16 = op == torch.float16                            # P and O are rounded to the operand format
+    assert bool((err <= ((4e-3 + 4e-3 * ref.abs()) if f16 else (2e-2 + 2e-2 * ref.abs()))).all()), float(err.max())
+    assert float(err.mean()) < (6e-4 if f16 else 3e-3)

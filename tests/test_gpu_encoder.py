@@ -1,6 +1,6 @@
 """GPU parity of AudioEncoder (through the C ABI) against the CPU oracle / reference fixtures.
-fp32 variant: <= 1e-4 max-abs.  bf16 variant: allclose(atol=2e-2, rtol=1e-2) vs the fp32
-oracle (BASELINE.json north_star)."""
+fp32 variant: <= 1e-4 max-abs.  Tensor-core variant (compute="bf16": 16-bit MMA operands, bf16 hidden states):
+allclose(atol=2e-2, rtol=1e-2) vs the fp32 oracle, every element (BASELINE.json north_star)."""
 import json
 import os
 
@@ -95,32 +95,52 @@ def test_full_size_64x30s_batch_properties(ab):
     assert float((inner - inner[0]).abs().max()) <= 2.5e-2                # one bf16 rounding of values up to ~4
 
 
-def _check_bf16(err, ref, what, scale=1.0):
-    """bf16 criterion (DESIGN.md 'Numerics').  The contract reads 2e-2 max-abs / 1e-2 relative vs the
-    fp32 reference.  With bf16 GEMM operands the strict elementwise form is out of reach even for
-    ideal numerics (2.1-2.8e-2), and the reference's OWN bf16 autocast sits at
-    5.1e-2 max-abs / 1.3e-2 of abs-max.  So the gate is: essentially every
-    element inside allclose(atol=2e-2, rtol=1e-2), and max error no worse than the reference's own
-    bf16 envelope; the strict numbers are printed."""
-    tol = scale * (2e-2 + 1e-2 * ref.abs())
-    outside = float((err > tol).float().mean())
+def test_config2_with_transformer_layer_at_full_length(ab):
+    """BASELINE config 2 model with enc=True at the full 30 s frame count (T = 3001: 24 key tiles per query tile in the
+    flash attention, ragged last tile), two clips against the oracle."""
+    sd = oracle.random_encoder_state_dict(80, 512, 4, True, seed=21, perturb=False)
+    waves = synth.make_batch("WH", 480000)
+    mel = oracle.log_mel_batch(waves, 80, 400)
+    ref = oracle.audio_encoder_forward(sd, mel, 4)
+    y = _enc(ab, sd, 80, 512, 4, 4, True, "bf16")(mel.cuda()).float().cpu()
+    _check_bf16((y - ref).abs(), ref, "config 2, enc=True, T=3001")
+
+
+@pytest.mark.parametrize("enc", [False, True])
+def test_config4_wide_encoder_at_depth(ab, enc):
+    """BASELINE config 4 model (D=1024, H=16, L=24) at full depth and full length, one clip against the oracle."""
+    sd = oracle.random_encoder_state_dict(80, 1024, 24, enc, seed=22, perturb=False)
+    waves = synth.make_batch("H", 480000)
+    mel = oracle.log_mel_batch(waves, 80, 400)
+    ref = oracle.audio_encoder_forward(sd, mel, 16)
+    y = _enc(ab, sd, 80, 1024, 16, 24, enc, "bf16")(mel.cuda()).float().cpu()
+    _check_bf16((y - ref).abs(), ref, f"config 4, L=24, T=3001, enc={enc}")
+
+
+def _check_bf16(err, ref, what):
+    """The contract of BASELINE.json's north_star for the tensor-core variant: encoder hidden states within 2e-2 max-abs /
+    1e-2 relative of the fp32 reference, read as torch.allclose(atol=2e-2, rtol=1e-2) -- EVERY
+    element inside, no escape hatch.  Strict max-abs, max-abs / abs-max and the worst error / tolerance ratio are printed
+    (tools/numerics_study.py predicts <= 0.45 for fp16 MMA operands; bf16 operands sit at 1.5-2.7 and cannot pass)."""
+    tol = 2e-2 + 1e-2 * ref.abs()
+    outside = int((err > tol).sum())
+    worst = float((err / tol).max())
     rel = float(err.max() / ref.abs().max())
     fro = float(err.norm() / ref.norm())
-    print(f"bf16 {what}: max-abs {float(err.max()):.4f}  max-abs/absmax {rel:.5f}  frobenius-rel {fro:.5f}  outside-allclose {outside:.2e}")
-    assert outside <= 2e-4, outside
-    assert fro <= 5e-3 * scale, fro
-    assert rel <= 1.3e-2 * scale, rel
-    assert float(err.max()) <= 5.1e-2 * scale * max(1.0, float(ref.abs().max()) / 4.0), float(err.max())
+    print(f"bf16 {what}: max-abs {float(err.max()):.4f}  max-abs/absmax {rel:.5f}  frobenius-rel {fro:.5f}  "
+          f"worst err/tol {worst:.3f}  outside-allclose {outside}")
+    assert outside == 0, (outside, worst)
+    assert fro <= 3e-3, fro
 
 
-def test_bf16_wide_model_runs_unfused_layernorm(ab):
-    """D=1024 (BASELINE config 4 width): LayerNorm rows do not fit TMEM, unfused path."""
+def test_bf16_wide_model(ab):
+    """D=1024 (BASELINE config 4 width), one block + TransformerEncoderLayer."""
     sd = oracle.random_encoder_state_dict(80, 1024, 1, True, seed=4, perturb=False)
     waves = synth.make_batch("WH", 200 * 160)
     mel = oracle.log_mel_batch(waves, 80, 400)
     ref = oracle.audio_encoder_forward(sd, mel, 16)
     y = _enc(ab, sd, 80, 1024, 16, 1, True, "bf16")(mel.cuda()).float().cpu()
-    _check_bf16((y - ref).abs(), ref, "D=1024 unfused LN", scale=2.0)        # one extra bf16 rounding (DESIGN.md)
+    _check_bf16((y - ref).abs(), ref, "D=1024")
 
 
 def test_conv2_single_channel_stream_bf16(ab):
@@ -184,15 +204,13 @@ def test_three_streams_in_one_pass_equal_three_calls(ab, compute):
     (80, 768, 6, 1, True, 2, 260), (80, 1024, 16, 1, False, 1, 400)])
 def test_bf16_other_widths_and_small_shapes(ab, mels, D, H, L, enc, B, T):
     """Widths with 1, 3, 5, 6, 8 channel tiles (the persistent kernels then change channel tile between units), T below one
-    tile, 128 mels: relative criteria only (max-abs scales with the activations' range)."""
+    tile, 128 mels."""
     sd = oracle.random_encoder_state_dict(mels, D, L, enc, seed=D, perturb=True)
     x = torch.randn(B, mels, T, generator=torch.Generator().manual_seed(T))
     ref = oracle.audio_encoder_forward(sd, x, H)
     y = _enc(ab, sd, mels, D, H, L, enc, "bf16")(x.cuda()).float().cpu()
-    d = (y - ref).abs()
     assert not torch.isnan(y).any()
-    assert float(d.max() / ref.abs().max()) <= 1.3e-2
-    assert float((d > 2e-2 + 1e-2 * ref.abs()).float().mean()) <= 4e-4
+    _check_bf16((y - ref).abs(), ref, f"mels={mels} D={D} enc={enc} T={T}")
 
 
 def test_weight_update_invalidates_the_packed_copy(ab):

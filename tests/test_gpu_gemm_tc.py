@@ -1,5 +1,5 @@
 """The tcgen05/TMEM/TMA implicit-GEMM kernel in isolation (asrb_test_gemm_tc) against a plain
-PyTorch fp32 reference of the same op on the same bf16-rounded operands."""
+PyTorch fp32 reference of the same op on the same 16-bit-rounded operands (the library's operand format)."""
 import pytest
 import torch
 import torch.nn.functional as F
@@ -90,12 +90,13 @@ CASES = [
 @pytest.mark.parametrize("B,T,K,N,taps,epi,act", CASES)
 def test_gemm_tc_matches_torch(built_lib, B, T, K, N, taps, epi, act):
     lib = built_lib.load()
+    op = built_lib.operand_dtype()
     g = torch.Generator(device="cuda").manual_seed(B * 1000 + T + K + N + taps + epi)
-    a = (torch.randn(B, T, K, device="cuda", generator=g) * 0.5).bfloat16()
-    w = (torch.randn(N, taps * K, device="cuda", generator=g) / (taps * K) ** 0.5).bfloat16()
+    a = (torch.randn(B, T, K, device="cuda", generator=g) * 0.5).to(op)
+    w = (torch.randn(N, taps * K, device="cuda", generator=g) / (taps * K) ** 0.5).to(op)
     bias = torch.randn(N, device="cuda", generator=g) * 0.1
     n_out = N // 2 if epi in (1, 4) else N
-    res = (torch.randn(B, T, n_out, device="cuda", generator=g)).bfloat16() if epi in (2, 3, 5) and (T % 2 == 0 or epi != 3) else None
+    res = (torch.randn(B, T, n_out, device="cuda", generator=g)).to(op) if epi in (2, 3, 5) and (T % 2 == 0 or epi != 3) else None
     gamma = 1 + 0.2 * torch.randn(N, device="cuda", generator=g)
     beta = 0.1 * torch.randn(N, device="cuda", generator=g)
     dw = None
@@ -109,7 +110,7 @@ def test_gemm_tc_matches_torch(built_lib, B, T, K, N, taps, epi, act):
         dw = (dw_w, dw_b, kw, act2, pos)
         dw_args = (dw_w.data_ptr(), dw_b.data_ptr(), kw, act2, pos.data_ptr() if pos is not None else None)
     guard = 64 * n_out                                  # sentinel rows before and after: nothing may be written outside the tensor
-    buf = torch.full((B * T * n_out + 2 * guard,), 12345.0, device="cuda", dtype=torch.bfloat16)
+    buf = torch.full((B * T * n_out + 2 * guard,), 12345.0, device="cuda", dtype=op)
     out = buf[guard: guard + B * T * n_out].view(B, T, n_out)
     out.fill_(float("nan"))
     rc = lib.asrb_test_gemm_tc(a.data_ptr(), w.data_ptr(), bias.data_ptr(), res.data_ptr() if res is not None else None,
@@ -120,6 +121,8 @@ def test_gemm_tc_matches_torch(built_lib, B, T, K, N, taps, epi, act):
     assert not torch.isnan(out.float()).any(), "rows were left unwritten"
     assert bool((buf[:guard] == 12345.0).all()) and bool((buf[-guard:] == 12345.0).all()), "wrote outside the output tensor"
     err = (out.float() - ref).abs()
-    tol = 2e-2 + 1e-2 * ref.abs()                      # bf16 store rounding dominates
+    # the store rounding dominates (fp16: 2^-11 relative; bf16: 2^-8), then the MUFU-based activations (2.5e-4 |x| each)
+    tol = (4e-3 + 2e-3 * ref.abs()) if op == torch.float16 else (2e-2 + 1e-2 * ref.abs())
+    print(f"gemm_tc epi={epi}: max err {float(err.max()):.5f}  worst err/tol {float((err / tol).max()):.3f}  mean {float(err.mean()):.6f}")
     assert bool((err <= tol).all()), f"max err {float(err.max())} at {int(err.argmax())}"
-    assert float(err.mean()) < 3e-3
+    assert float(err.mean()) < (6e-4 if op == torch.float16 else 3e-3)
