@@ -471,7 +471,7 @@ extern "C" size_t asrb_pcm_to_hidden_workspace_bytes(const asrb_logmel_plan* pl,
     if (!pl || !e || B < 0 || n_samples < 0) return 0;
     const int64_t T = 1 + n_samples / pl->hop;
     return enc_ws_bytes(e, B, T) + align_up(sizeof(float) * (size_t)B * pl->n_mels * T, 256) +
-           align_up(sizeof(uint32_t) * (size_t)(B > 0 ? B : 1), 256) + 256;
+           align_up(sizeof(uint32_t) * logmel_keys_words(pl, B, n_samples), 256) + 256;
 }
 
 extern "C" int asrb_pcm_to_hidden(const asrb_logmel_plan* pl, asrb_encoder* e, const float* pcm, int64_t B,
@@ -493,7 +493,7 @@ extern "C" int asrb_pcm_to_hidden(const asrb_logmel_plan* pl, asrb_encoder* e, c
     EncBuffers w = carve(e, B, T, ws, enc_bytes);
     Arena tail((char*)ws + enc_bytes, ws_bytes - enc_bytes);
     float* mel = logmel_out ? logmel_out : tail.take<float>((size_t)B * pl->n_mels * T);
-    uint32_t* keys = tail.take<uint32_t>((size_t)B);
+    uint32_t* keys = tail.take<uint32_t>(logmel_keys_words(pl, B, n_samples));
     if (!w.ok || !tail.ok()) return fail(ASRB_E_WORKSPACE, "asrb_pcm_to_hidden: workspace carve failed");
     const bool bf = e->cfg.compute == ASRB_BF16;
     if (bf && !logmel_out) {

@@ -2,18 +2,26 @@
 // real FFT + |X|^2 + HTK mel projection + log10/clamp/normalise in ONE pass over the PCM.
 //
 // Data layout in HBM:  pcm [B][stride] fp32 (read once, staged in shared memory where the
-// 2.5x / 6.4x frame overlap lives);  out [B][M][T] fp32 (written once);  keys [B] uint32 --
-// order-preserving image of each utterance's running max of log10(mel).
+// 2.5x / 6.4x frame overlap lives);  out [B][M][T] fp32 (written once) or, on the fused path, the stem
+// GEMM's operand [B][T][CP] in the 16-bit operand format;  keys [B] uint32 -- order-preserving image of
+// each utterance's running max of log10(mel);  optionally pool_out [B][target]: the average-pooled
+// `waveform` feature (essentials.py:493-503), taken from the PCM span this pass has staged anyway.
 //
-// One block = FB consecutive frames of one utterance.  Two real frames ride one complex
-// FFT (z = a + i b); an N = R*R point FFT is two rounds of R-point DFTs held in registers
-// (R threads per FFT, R = 20 for n_fft 400, 32 for n_fft 1024) with one transpose through
-// shared memory in between.  The per-utterance dynamic-range floor (max - 8) needs the max
-// of the WHOLE utterance, so this pass writes (log10 + 4) / 4 and publishes the max with
-// one atomicMax per block; logmel_floor_kernel then raises the values below the floor
-// (monotone, so max((x+4)/4, (floor+4)/4) == (max(x, floor)+4)/4 bit for bit) and only
-// writes where something changes.
+// One block = FB consecutive frames of one utterance; a thread group of R threads owns a QUAD of four
+// consecutive frames.  Two real frames ride one complex FFT (z = a + i b) and a thread carries TWO such FFTs
+// side by side in the two lanes of packed f32x2 registers (fft_regs.cuh), so the whole transform issues as
+// FADD2 / FMUL2 / FFMA2.  An N = R*R point FFT is two rounds of R-point DFTs held in registers (R = 20 for
+// n_fft 400, 32 for n_fft 1024) with one transpose through shared memory in between (16-byte accesses, odd
+// pitches: conflict free).  The conjugate-symmetric partner Z[N-k] that the split of the packed pair needs
+// lives in exactly one other thread (R - j), so only the upper half of the spectrum is exchanged.  Power
+// spectra go to shared memory as [bin][frame] rows; the banded mel projection reads them back four frames at
+// a time (one LDS.128 + two FFMA2 per tap), then MUFU lg2.
+// The per-utterance dynamic-range floor (max - 8) needs the max of the WHOLE utterance, so this pass writes
+// (log10 + 4) / 4 and publishes the max with one atomicMax per block; logmel_floor_kernel then raises the
+// values below the floor (monotone, so max((x+4)/4, (floor+4)/4) == (max(x, floor)+4)/4 bit for bit) and
+// only writes where something changes.
 #include "logmel.cuh"
+#include "tc_common.cuh"
 #include "fft_regs.cuh"
 #include <vector>
 #include <cmath>
@@ -27,23 +35,37 @@ struct LogmelParams {
     const float2* twiddle;     // [R][R]: W_N^(k1*j) at [k1*R + j]
     const int* mel_lo;         // [M] first bin of filter m
     const int* mel_cnt;        // [M] taps (0 for an all-zero filter)
-    const float* mel_w;        // [M][kmax]
+    const float* mel_w;        // [M][kmax], scaled by 1/4 (the split of the packed pair leaves 2 Re, 2 Im)
     float* out;                // [B][M][T] fp32 (reference layout), or NULL with out_cl set
     op16* out_cl;              // fused path: [B][T][CP] op16 channels-last, channels >= M zero (the stem GEMM's operand)
     int CP;
     uint32_t* keys;            // [B]
+    uint32_t* tile_min;        // [B * tiles_per_utt]: order-preserving image of each tile's smallest log10(mel) (the floor pass skips tiles above the floor)
+    float* pool_out;           // optional [B][pool_target]: adaptive average pooling of the PCM (essentials.py:493-503)
+    int64_t pool_target;
 };
 
-template <int NFFT, int R, int FB>
+template <int NFFT, int R, int FB, int HOP>
 struct LogmelCfg {
-    static constexpr int N = NFFT;
-    static constexpr int GROUPS = FB / 2;              // complex FFTs per block
-    static constexpr int THREADS = GROUPS * R;
+    static constexpr int QUADS = FB / 4;               // frame quads = thread groups per block
+    static constexpr int THREADS = QUADS * R;
     static constexpr int NB = NFFT / 2 + 1;            // one-sided bins
-    static constexpr int YSTRIDE = R * (R + 1);        // float2 per group (padded transpose)
-    static constexpr int BINS_PER_THREAD = (NB + R - 1) / R;
+    static constexpr int YP = R + 1, EP = R / 2 + 1;   // row pitches in float4 (odd: 16-byte accesses are conflict free)
+    static constexpr int Y_BYTES = QUADS * R * YP * 16;
+    static constexpr int E_BYTES = QUADS * R * EP * 16;
+    static constexpr int PP = FB + 4;                  // floats per power row (pitch 9 / 5 chunks of 16 B)
+    static constexpr int P_ROWS = NB + 4;              // zero-weight padding taps read up to 3 rows past the last bin
+    static constexpr int P_BYTES = P_ROWS * PP * 4;
+    static constexpr int REGION = Y_BYTES > E_BYTES + P_BYTES ? Y_BYTES : E_BYTES + P_BYTES;
+    // hop = 160, R = 20: the four frames of a quad start 640 samples = 0 banks apart from the next quad, whose
+    // first 12 threads share a warp with this quad's 20: a gap of 20 words per quad in the staged span puts them on
+    // the 12 banks the first 20 leave free.  640 is a multiple of R, so which side of a gap a sample falls on is a
+    // compile-time property of (frame in quad, n1).
+    static constexpr bool SKEW = HOP == 160 && R == 20;
+    static constexpr int GAP = SKEW ? 20 : 0;
     static_assert(R * R == NFFT, "two-round FFT needs n_fft = R^2");
-    static_assert(FB * NB <= GROUPS * YSTRIDE * 2, "power spectra must fit over the FFT buffer");
+    static_assert(E_BYTES + NB * PP * 4 >= Y_BYTES, "the transpose buffer must not reach the power rows' zero padding");
+    static_assert((QUADS & (QUADS - 1)) == 0, "frame quads per block: a power of two");
 };
 
 // cp.async with zero fill: copies `bytes` (0..size) from src and zero-fills the rest of `size`
@@ -56,226 +78,348 @@ __device__ __forceinline__ void cp_async4(uint32_t dst, const void* src, int byt
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// Persistent: gridDim.x blocks walk the (utterance, frame-tile) list; constants are staged once
-// per block and the PCM span of the NEXT tile streams in with cp.async (zero fill outside
-// [0, len) = the center=True padding) while the current tile is transformed.
-template <int NFFT, int R, int FB>
-__global__ void __launch_bounds__(LogmelCfg<NFFT, R, FB>::THREADS)
-logmel_kernel(const LogmelParams p, int tiles_per_utt, int total_tiles) {
-    using C = LogmelCfg<NFFT, R, FB>;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int span = (FB - 1) * p.hop + NFFT;
-    const int span4 = (span + 3) & ~3;
-    float*  s_pcm0 = reinterpret_cast<float*>(smem_raw);                // [2][span4]
-    float*  s_win = s_pcm0 + 2 * span4;                                 // [NFFT]
-    float2* s_tw  = reinterpret_cast<float2*>(s_win + NFFT);            // [R*R]
-    float2* s_y   = s_tw + R * R;                                       // [GROUPS][YSTRIDE]
-    float*  s_pow = reinterpret_cast<float*>(s_y);                      // aliases s_y: [FB][NB]
-    float*  s_melw = reinterpret_cast<float*>(s_y + C::GROUPS * C::YSTRIDE);   // [M][kmax]
-    int*    s_lo  = reinterpret_cast<int*>(s_melw + p.M * p.kmax);      // [M]
-    int*    s_cnt = s_lo + p.M;                                         // [M]
-    // fused path: the tile's [FB][CP] 16-bit output is transposed through shared memory (pitch CP + 2 halves:
-    // frame-per-lane writes and row reads are both conflict free)
-    op16* s_cl = reinterpret_cast<op16*>(s_cnt + p.M + (p.M & 1));
-    const int clp = p.CP + 2;
-    __shared__ float s_red[32];
+__device__ __forceinline__ float4 pack4(const cx2& z) { return make_float4(z.re.x, z.re.y, z.im.x, z.im.y); }
+__device__ __forceinline__ cx2 unpack4(const float4& v) { return {make_float2(v.x, v.y), make_float2(v.z, v.w)}; }
 
-    const int tid = threadIdx.x;
-    const bool vec_ok = ((p.stride & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.pcm) & 15) == 0) && ((p.hop & 3) == 0);
-
-    auto prefetch = [&](int tile, float* dstbuf) {       // async copy of one tile's PCM span
-        const int b = tile / tiles_per_utt, t0 = (tile - b * tiles_per_utt) * FB;
-        const int64_t len = clamp_len(p.lengths, b, p.n_samples);
-        const float* src = p.pcm + (int64_t)b * p.stride;
-        const int64_t s0 = (int64_t)t0 * p.hop - NFFT / 2;
-        const uint32_t d0 = (uint32_t)__cvta_generic_to_shared(dstbuf);
-        if (vec_ok) {                                     // s0 is a multiple of 4 here
-            for (int i = tid * 4; i < span4; i += C::THREADS * 4) {
-                const int64_t sidx = s0 + i;
-                int64_t valid = len - sidx;               // samples available from sidx
-                valid = valid < 0 ? 0 : (valid > 4 ? 4 : valid);
-                const bool in = sidx >= 0 && valid > 0;   // sidx < 0: whole chunk is padding (sidx multiple of 4)
-                cp_async16(d0 + 4u * i, in ? (const void*)(src + sidx) : (const void*)src, in ? (int)valid * 4 : 0);
-            }
-        } else {
-            for (int i = tid; i < span4; i += C::THREADS) {
-                const int64_t sidx = s0 + i;
-                const bool in = sidx >= 0 && sidx < len;
-                cp_async4(d0 + 4u * i, in ? (const void*)(src + sidx) : (const void*)p.pcm, in ? 4 : 0);
-            }
-        }
-        cp_async_commit();
-    };
-
-    int tile = blockIdx.x;
-    if (tile < total_tiles) prefetch(tile, s_pcm0);
-    // ---- constants, once per block ----
-    for (int i = tid; i < NFFT; i += C::THREADS) s_win[i] = p.window[i];
-    for (int i = tid; i < R * R; i += C::THREADS) s_tw[i] = p.twiddle[i];
-    for (int i = tid; i < p.M * p.kmax; i += C::THREADS) s_melw[i] = p.mel_w[i];
-    for (int i = tid; i < p.M; i += C::THREADS) { s_lo[i] = p.mel_lo[i]; s_cnt[i] = p.mel_cnt[i]; }
-    if (p.out_cl) for (int i = tid; i < FB * clp; i += C::THREADS) s_cl[i] = to_op16(0.f);   // channels >= M stay 0
-
-    const int g = tid / R, j = tid - g * R;
-    float2* yg = s_y + g * C::YSTRIDE;
-    const int lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // provably warp-uniform: filter loops run on the uniform datapath
-    constexpr int nwarp = C::THREADS / 32;
-    constexpr int FW = FB < 32 ? FB : 32;                   // frames handled by one warp pass
-    constexpr int MSUB = 32 / FW;                           // filters handled side by side
-
-    for (int it = 0; tile < total_tiles; tile += gridDim.x, ++it) {
-        float* s_pcm = s_pcm0 + (it & 1) * span4;
-        const int next = tile + gridDim.x;
-        if (next < total_tiles) { prefetch(next, s_pcm0 + ((it + 1) & 1) * span4); cp_async_wait<1>(); }
-        else cp_async_wait<0>();
-        __syncthreads();                                    // this tile's PCM (and the constants) are visible
-
-        const int b = tile / tiles_per_utt, t0 = (tile - b * tiles_per_utt) * FB;
-        const int64_t len = clamp_len(p.lengths, b, p.n_samples);
-        const int Tb = 1 + (int)(len / p.hop);              // valid frames of this utterance (<= T: len <= n_samples)
-
-        // ---- round 1: R-point DFT over n1 of z[R n1 + j], twiddle W_N^(j k1), transpose ----
-        {
-            float2 x[R];
-            const float* fa = s_pcm + (2 * g) * p.hop;
-            const float* fb = fa + p.hop;
+// N taps-of-four of one filter against four frames' power rows: every load is issued before the first FFMA2
+template <int N, int PP>
+__device__ __forceinline__ void mel_taps(const float* px, const float4* w4, V2& a01, V2& a23) {
+    float4 w[N], pv[N][4];
 #pragma unroll
-            for (int n1 = 0; n1 < R; ++n1) {
-                const int n = R * n1 + j;
-                const float w = s_win[n];
-                x[n1] = make_float2(w * fa[n], w * fb[n]);
-            }
-            SmallDFT<R>::run(x);
-            yg[j] = x[0];
+    for (int t = 0; t < N; ++t) {
+        w[t] = w4[t];
 #pragma unroll
-            for (int k1 = 1; k1 < R; ++k1) yg[k1 * (R + 1) + j] = cmul(x[k1], s_tw[k1 * R + j]);
-        }
-        __syncthreads();
-
-        // ---- round 2: thread k1 = j does the R-point DFT over n2 -> Z[j + R k2] ----
-        {
-            float2 y[R];
+        for (int i = 0; i < 4; ++i) pv[t][i] = *reinterpret_cast<const float4*>(px + (4 * t + i) * PP);
+    }
 #pragma unroll
-            for (int n2 = 0; n2 < R; ++n2) y[n2] = yg[j * (R + 1) + n2];
-            SmallDFT<R>::run(y);
-            __syncthreads();                                // everyone has read the transpose
+    for (int t = 0; t < N; ++t) {
+        const float ws[4] = {w[t].x, w[t].y, w[t].z, w[t].w};
 #pragma unroll
-            for (int k2 = 0; k2 < R; ++k2) yg[j + R * k2] = y[k2];
-        }
-        __syncthreads();
-
-        // ---- split the packed pair: A[k] = (Z[k] + conj Z[N-k]) / 2, B[k] = (Z[k] - conj Z[N-k]) / 2i ----
-        float pa[C::BINS_PER_THREAD], pb[C::BINS_PER_THREAD];
-#pragma unroll
-        for (int i = 0; i < C::BINS_PER_THREAD; ++i) {
-            const int k = j + R * i;
-            pa[i] = pb[i] = 0.f;
-            if (k < C::NB) {
-                const float2 z1 = yg[k];
-                const float2 z2 = yg[k == 0 ? 0 : NFFT - k];
-                const float ar = z1.x + z2.x, ai = z1.y - z2.y;     // 2 Re A, 2 Im A
-                const float br = z1.y + z2.y, bi = z2.x - z1.x;     // 2 Re B, 2 Im B
-                pa[i] = 0.25f * fmaf(ar, ar, ai * ai);
-                pb[i] = 0.25f * fmaf(br, br, bi * bi);
-            }
-        }
-        __syncthreads();                                    // Z is dead: reuse it for |X|^2
-#pragma unroll
-        for (int i = 0; i < C::BINS_PER_THREAD; ++i) {
-            const int k = j + R * i;
-            if (k < C::NB) {
-                s_pow[(2 * g) * C::NB + k] = pa[i];
-                s_pow[(2 * g + 1) * C::NB + k] = pb[i];
-            }
-        }
-        __syncthreads();
-
-        // ---- banded mel projection + log10 + (x+4)/4; lane -> frame so stores are coalesced ----
-        const int f = lane % FW;
-        float vmax = -INFINITY;
-        for (int fbase = 0; fbase < FB; fbase += FW) {
-            const int fr = fbase + f;
-            const int t = t0 + fr;
-            const float* pw = s_pow + fr * C::NB;
-            for (int m = warp * MSUB + lane / FW; m < p.M; m += nwarp * MSUB) {
-                // banded filter, taps zero-padded to a multiple of 4: one broadcast 16-byte weight load per 4 taps
-                const int lo = s_lo[m], n4 = (s_cnt[m] + 3) >> 2;
-                const float4* w4 = reinterpret_cast<const float4*>(s_melw + m * p.kmax);
-                const float* px = pw + lo;
-                float acc = 0.f;
-#pragma unroll 1                                               // 1-3 trips: remainder code of an unrolled loop costs more than it saves
-                for (int q = 0; q < n4; ++q) {
-                    const float4 w = w4[q];
-                    acc = fmaf(w.x, px[4 * q], acc);
-                    acc = fmaf(w.y, px[4 * q + 1], acc);
-                    acc = fmaf(w.z, px[4 * q + 2], acc);
-                    acc = fmaf(w.w, px[4 * q + 3], acc);
-                }
-                // log10 through MUFU lg2 (abs error ~2^-22 in log2: 7e-8 in log10)   essentials.py:488
-                float lg;                                                   // argument >= 1e-10: never denormal, plain MUFU.LG2
-                asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(fmaxf(acc, 1e-10f)));
-                lg *= 0.30102999566398120f;
-                if (t < p.T) {
-                    float sv = 0.f;                                         // DataCollator pad value
-                    if (t < Tb) { vmax = fmaxf(vmax, lg); sv = (lg + 4.0f) / 4.0f; }   // essentials.py:490
-                    if (p.out_cl) s_cl[fr * clp + m] = to_op16(sv);
-                    else p.out[((int64_t)b * p.M + m) * p.T + t] = sv;
-                }
-            }
-        }
-        vmax = warp_max(vmax);
-        if (lane == 0) s_red[warp] = vmax;
-        __syncthreads();                                    // also: s_pow / s_pcm are free for the next tile
-        if (p.out_cl) {                                     // rows of CP 16-bit values, two per 32-bit word: coalesced
-            const int wpr = p.CP >> 1;
-            uint32_t* dst = reinterpret_cast<uint32_t*>(p.out_cl + ((int64_t)b * p.T + t0) * p.CP);
-            for (int i = tid; i < FB * wpr; i += C::THREADS) {
-                const int fr = i / wpr, w = i - fr * wpr;
-                if (t0 + fr < p.T) dst[i] = *reinterpret_cast<const uint32_t*>(s_cl + fr * clp + 2 * w);
-            }
-        }
-        if (warp == 0) {
-            float v = lane < nwarp ? s_red[lane] : -INFINITY;
-            v = warp_max(v);
-            if (lane == 0 && v > -INFINITY) atomicMax(p.keys + b, f2key(v));
+        for (int i = 0; i < 4; ++i) {
+            a01 = vfma(ws[i], make_float2(pv[t][i].x, pv[t][i].y), a01);
+            a23 = vfma(ws[i], make_float2(pv[t][i].z, pv[t][i].w), a23);
         }
     }
 }
 
-// essentials.py:489: log_mel = maximum(log_mel, log_mel.max() - 8.0), applied in the
-// normalised domain.  Touches memory only where the floor is active.
-__global__ void logmel_floor_kernel(float* out, const uint32_t* keys, const int32_t* lengths,
-                                    int64_t n_samples, int hop, int M, int T) {
-    const int b = blockIdx.y;
-    const int64_t len = clamp_len(lengths, b, n_samples);
-    const int Tb = 1 + (int)(len / hop);
-    const float floor_s = ((key2f(keys[b]) - 8.0f) + 4.0f) / 4.0f;
-    float* o = out + (int64_t)b * M * T;
-    const int64_t total = (int64_t)M * T;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-         i += (int64_t)gridDim.x * blockDim.x) {
-        const int t = (int)(i % T);
-        if (t < Tb) {
-            const float v = o[i];
-            if (v < floor_s) o[i] = floor_s;
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {     // TMA 1-D bulk copy
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+// Persistent: gridDim.x blocks walk the (utterance, frame-tile) list; constants are staged once per block and the
+// PCM span of the NEXT tile streams in with cp.async (zero fill outside [0, len) = the center=True padding) while
+// the current tile is transformed.  HOP = 0: hop is a run-time value (no bank skew).
+template <int NFFT, int R, int FB, int HOP>
+__global__ void __launch_bounds__(LogmelCfg<NFFT, R, FB, HOP>::THREADS)
+logmel_kernel(const LogmelParams p, int tiles_per_utt, int total_tiles) {
+    using C = LogmelCfg<NFFT, R, FB, HOP>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int hop = HOP ? HOP : p.hop;
+    const int span = (FB - 1) * hop + NFFT;
+    const int span4 = (span + 3) & ~3;
+    const int pcm_words = span4 + C::GAP * C::QUADS + 4;
+    // region: Y (transpose) | E (partner exchange) + P (power rows); E doubles as the fused path's output staging
+    float4* s_y   = reinterpret_cast<float4*>(smem_raw);
+    float4* s_e   = reinterpret_cast<float4*>(smem_raw);
+    float*  s_p   = reinterpret_cast<float*>(smem_raw + C::E_BYTES);
+    op16*   s_cl  = reinterpret_cast<op16*>(smem_raw);
+    float*  s_pcm = reinterpret_cast<float*>(smem_raw + C::REGION);            // [pcm_words]
+    float*  s_win = s_pcm + pcm_words;                                          // [NFFT]
+    float2* s_tw  = reinterpret_cast<float2*>(s_win + NFFT);                    // [R*R]
+    float*  s_melw = reinterpret_cast<float*>(s_tw + R * R);                    // [M][kmax]
+    int*    s_lo  = reinterpret_cast<int*>(s_melw + p.M * p.kmax);              // [M]
+    int*    s_n4  = s_lo + p.M;                                                 // [M] taps / 4, rounded up
+    __shared__ float s_red[64];
+    __shared__ __align__(8) uint64_t s_bar;                                     // completion of the TMA-fetched PCM span
+
+    const int tid = threadIdx.x;
+    const bool vec_ok = ((p.stride & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.pcm) & 15) == 0) && ((hop & 3) == 0);
+    const int clp = p.CP + 2;                                // staging pitch in 16-bit words: odd word count, conflict-free transposed writes
+
+    auto pos = [&](int s) { return C::SKEW ? s + C::GAP * (s / (4 * 160)) : s; };       // span index -> shared-memory word
+    // Async copy of one tile's PCM span; everything past the utterance (and before sample 0) is zero filled.  All index
+    // arithmetic is 32-bit and relative to the span; with the bank skew a thread's chunk in round `it` lies in quad `it`
+    // (THREADS * 4 samples = one quad of hops), so the gap offset is a compile-time constant per round.
+    // A tile whose whole span lies inside the utterance (all but the first and the last two of an utterance) is fetched by
+    // ONE thread with TMA bulk copies (one per frame quad when the bank skew is on) that complete on an mbarrier; the edge
+    // tiles, which need zero fill, go through cp.async.
+    auto tile_geom = [&](int tile, int& b, int& t0, int64_t& s0, int& lo, int& hi) {
+        b = tile / tiles_per_utt; t0 = (tile - b * tiles_per_utt) * FB;
+        const int64_t len = clamp_len(p.lengths, b, p.n_samples);
+        s0 = (int64_t)t0 * hop - NFFT / 2;
+        lo = s0 < 0 ? (int)(-s0) : 0;                                              // first span index that is a real sample
+        const int64_t rem = len - s0;
+        hi = rem < 0 ? 0 : (rem > span4 ? span4 : (int)rem);                       // one past the last real sample
+    };
+    const uint32_t pcm_bar = (uint32_t)__cvta_generic_to_shared(&s_bar);
+    const uint32_t d0 = (uint32_t)__cvta_generic_to_shared(s_pcm);
+    auto prefetch = [&](int tile) -> bool {                                        // returns: fetched by TMA (wait on the mbarrier)
+        int b, t0, lo, hi; int64_t s0;
+        tile_geom(tile, b, t0, s0, lo, hi);
+        const float* src = p.pcm + (int64_t)b * p.stride + s0;                     // span index 0 (never dereferenced outside [lo, hi))
+        if (vec_ok && lo == 0 && hi == span4) {
+            if (tid == 0) {
+                mbar_expect_tx(pcm_bar, (uint32_t)span4 * 4u);
+                if (C::SKEW) {
+                    for (int c = 0; c * 640 < span4; ++c) {
+                        const int n = span4 - c * 640 < 640 ? span4 - c * 640 : 640;
+                        bulk_g2s(d0 + 4u * (uint32_t)(c * (640 + C::GAP)), src + c * 640, (uint32_t)n * 4u, pcm_bar);
+                    }
+                } else bulk_g2s(d0, src, (uint32_t)span4 * 4u, pcm_bar);
+            }
+            return true;
+        }
+        if (vec_ok) {
+            for (int i = tid * 4; i < span4; i += C::THREADS * 4) {
+                int valid = hi - i;                                               // samples available from i
+                valid = (i < lo || valid < 0) ? 0 : (valid > 4 ? 4 : valid);
+                // (a source size of 0 reads nothing: the address may lie outside the utterance)
+                cp_async16(d0 + 4u * (uint32_t)pos(i), (const void*)(src + i), valid * 4);
+            }
+        } else {
+            for (int i = tid; i < span4; i += C::THREADS) {
+                const bool in = i >= lo && i < hi;
+                cp_async4(d0 + 4u * pos(i), in ? (const void*)(src + i) : (const void*)p.pcm, in ? 4 : 0);
+            }
+        }
+        cp_async_commit();
+        return false;
+    };
+
+    int tile = blockIdx.x;
+    if (tid == 0) { mbar_init(pcm_bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    __syncthreads();
+    bool by_tma = false; uint32_t tma_phase = 0;
+    if (tile < total_tiles) by_tma = prefetch(tile);
+    // ---- constants, once per block ----
+    for (int i = tid; i < NFFT; i += C::THREADS) s_win[i] = p.window[i];
+    for (int i = tid; i < R * R; i += C::THREADS) s_tw[i] = p.twiddle[i];
+    for (int i = tid; i < p.M * p.kmax; i += C::THREADS) s_melw[i] = p.mel_w[i];
+    for (int i = tid; i < p.M; i += C::THREADS) { s_lo[i] = p.mel_lo[i]; s_n4[i] = (p.mel_cnt[i] + 3) >> 2; }
+    for (int i = tid; i < 4 * C::PP; i += C::THREADS) s_p[C::NB * C::PP + i] = 0.f;    // rows the zero-weight padding taps touch: finite
+
+    const int q = tid / R, j = tid - q * R;                  // frame quad, position inside the FFT
+    const int lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // provably warp-uniform
+    constexpr int nwarp = C::THREADS / 32;
+    float4* yq = s_y + q * (R * C::YP);
+    float4* eq = s_e + q * (R * C::EP);
+
+    for (; tile < total_tiles; tile += gridDim.x) {
+        if (by_tma) { mbar_wait(pcm_bar, tma_phase); tma_phase ^= 1u; } else cp_async_wait<0>();
+        __syncthreads();                                     // this tile's PCM (and the constants) are visible; the previous tile's readers are done
+
+        const int b = tile / tiles_per_utt, t0 = (tile - b * tiles_per_utt) * FB;
+        const int64_t len = clamp_len(p.lengths, b, p.n_samples);
+        const int Tb = 1 + (int)(len / hop);                 // valid frames of this utterance (<= T: len <= n_samples)
+
+        // ---- optional: the average-pooled `waveform` feature of the bins this tile's frames name.  Bin i covers
+        // samples [floor(i n / target), ceil((i + 1) n / target)): inside the staged span whenever n is a multiple
+        // of hop (then the bin IS one hop); whatever falls outside comes from global memory. ----
+        if (p.pool_out) {
+            const int64_t n = p.n_samples, tg = p.pool_target;
+            const int64_t s0 = (int64_t)t0 * hop - NFFT / 2;
+            const float* src = p.pcm + (int64_t)b * p.stride;
+            for (int i = warp; i < FB; i += nwarp) {
+                const int64_t bin = (int64_t)t0 + i;
+                if (bin >= tg) break;
+                const int64_t s = (bin * n) / tg, e = ((bin + 1) * n + tg - 1) / tg;
+                float acc = 0.f;
+                for (int64_t k = s + lane; k < e; k += 32) {
+                    const int64_t rel = k - s0;
+                    acc += (rel >= 0 && rel < span) ? s_pcm[pos((int)rel)] : src[k];
+                }
+                acc = warp_sum(acc);
+                if (lane == 0) p.pool_out[(int64_t)b * tg + bin] = acc / (float)(e - s);
+            }
+        }
+
+        // ---- round 1: window, R-point DFT over n1 of z[R n1 + j], twiddle W_N^(j k1), transpose ----
+        {
+            cx2 x[R];
+            // frames 4q .. 4q+3: (f0, f1) are the real parts of the two FFTs, (f2, f3) their imaginary parts
+            const float* fq = s_pcm + q * (4 * hop + C::GAP) + j;
+#pragma unroll
+            for (int n1 = 0; n1 < R; ++n1) {
+                const float w = s_win[R * n1 + j];
+                float v[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const bool wrap = C::SKEW && (i * 160 + R * n1 >= 4 * 160);       // past the quad's gap
+                    v[i] = fq[i * hop + R * n1 + (wrap ? C::GAP : 0)];
+                }
+                x[n1].re = vmul(w, make_float2(v[0], v[1]));
+                x[n1].im = vmul(w, make_float2(v[2], v[3]));
+            }
+            SmallDFT<R>::run(x);
+            yq[j] = pack4(x[0]);
+#pragma unroll
+            for (int k1 = 1; k1 < R; ++k1) {
+                const float2 tw = s_tw[k1 * R + j];
+                yq[k1 * C::YP + j] = pack4(cmul_cs(x[k1], tw.x, tw.y));
+            }
+        }
+        __syncthreads();                                     // everyone is done with the PCM span, too:
+        { const int next = tile + gridDim.x; if (next < total_tiles) by_tma = prefetch(next); }
+
+        // ---- round 2: thread k1 = j does the R-point DFT over n2 -> Z[j + R k2] ----
+        cx2 z[R];
+#pragma unroll
+        for (int n2 = 0; n2 < R; ++n2) z[n2] = unpack4(yq[j * C::YP + n2]);
+        SmallDFT<R>::run(z);
+        __syncthreads();                                     // everyone has read the transpose: E and P may overwrite it
+
+        // ---- conjugate partner exchange: Z[N - k] of k = j + R k2 (k2 < R/2) is thread (R - j)'s Z at
+        // k2' = R - 1 - k2 (thread 0: its own, at R - k2), i.e. always in an upper half ----
+#pragma unroll
+        for (int k2 = R / 2; k2 < R; ++k2) eq[j * C::EP + (k2 - R / 2)] = pack4(z[k2]);
+        eq[j * C::EP + R / 2] = pack4(z[0]);                 // thread 0's partner of k = 0 is Z[0] itself
+        __syncthreads();
+
+        // ---- split the packed pair: A[k] = (Z[k] + conj Z[N-k]) / 2, B[k] = (Z[k] - conj Z[N-k]) / 2i; |.|^2 of
+        // both for both FFTs = four frames of one bin -> one 16-byte store (the 1/4 lives in the mel weights) ----
+        {
+            const float4* ep = s_e + q * (R * C::EP) + (j ? R - j : 0) * C::EP + (j == 0 ? 1 : 0);
+            float* pk = s_p + j * C::PP + 4 * q;
+#pragma unroll
+            for (int k2 = 0; k2 < R / 2; ++k2) {
+                const cx2 z2 = unpack4(ep[R / 2 - 1 - k2]);
+                const V2 ar = vadd(z[k2].re, z2.re), ai = vsub(z[k2].im, z2.im);       // 2 Re A, 2 Im A
+                const V2 br = vadd(z[k2].im, z2.im), bi = vsub(z2.re, z[k2].re);       // 2 Re B, 2 Im B
+                const V2 pa = vfma2(ar, ar, vmul2(ai, ai)), pb = vfma2(br, br, vmul2(bi, bi));
+                *reinterpret_cast<float4*>(pk + (R * k2) * C::PP) = make_float4(pa.x, pa.y, pb.x, pb.y);
+            }
+            if (j == 0) {                                    // bin N/2 (self-conjugate): A = Re Z, B = Im Z
+                const V2 ar = vadd(z[R / 2].re, z[R / 2].re), br = vadd(z[R / 2].im, z[R / 2].im);
+                const V2 pa = vmul2(ar, ar), pb = vmul2(br, br);
+                *reinterpret_cast<float4*>(pk + (R * (R / 2)) * C::PP) = make_float4(pa.x, pa.y, pb.x, pb.y);
+            }
+        }
+        __syncthreads();
+
+        // ---- banded mel projection + log10 + (x+4)/4.  Work item = (filter m, frame quad): a thread keeps its quad and walks
+        // the filters R apart; the 8 (4) lanes that share m read one power row per tap, conflict free, and the weights arrive
+        // as broadcast 16-byte loads.  Taps go in groups of at most 3 x 4 with every load issued before the first FFMA2.
+        // Max / min are tracked on the raw lg2 values (scaling by log10(2) is monotone); sv = (log10 + 4) / 4 is one FMUL (to
+        // log10: keeps log10(1e-10) = -10 and hence silence = -1.5 exact) and one FFMA (essentials.py:488-490). ----
+        float vmax = -INFINITY, vmin = INFINITY;            // lg2 of the tile's largest / smallest mel value (valid frames)
+        {
+            const int qq = tid & (C::QUADS - 1);
+            const int tq = t0 + 4 * qq;                      // first frame of this thread's quad
+            const bool full = t0 + FB <= Tb;                 // every frame of the tile is a frame of the utterance (Tb <= T)
+            for (int m = tid / C::QUADS; m < p.M; m += R) {
+                int n4 = s_n4[m];
+                const float4* w4 = reinterpret_cast<const float4*>(s_melw + m * p.kmax);
+                const float* px = s_p + s_lo[m] * C::PP + 4 * qq;
+                V2 a01 = make_float2(0.f, 0.f), a23 = make_float2(0.f, 0.f);
+                while (n4 > 0) {
+                    if (n4 >= 3) mel_taps<3, C::PP>(px, w4, a01, a23);
+                    else if (n4 == 2) mel_taps<2, C::PP>(px, w4, a01, a23);
+                    else mel_taps<1, C::PP>(px, w4, a01, a23);
+                    n4 -= 3; w4 += 3; px += 12 * C::PP;
+                }
+                float lg[4] = {a01.x, a01.y, a23.x, a23.y};
+#pragma unroll
+                for (int i = 0; i < 4; ++i)                  // MUFU lg2 (abs error ~2^-22); the argument is >= 1e-10: never denormal
+                    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg[i]) : "f"(fmaxf(lg[i], 1e-10f)));
+                auto norm = [](float l2) { return fmaf(l2 * 0.30102999566398120f, 0.25f, 1.0f); };
+                if (full) {
+                    vmax = fmaxf(vmax, fmaxf(fmaxf(lg[0], lg[1]), fmaxf(lg[2], lg[3])));
+                    vmin = fminf(vmin, fminf(fminf(lg[0], lg[1]), fminf(lg[2], lg[3])));
+                    if (p.out_cl) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) s_cl[(4 * qq + i) * clp + m] = to_op16(norm(lg[i]));
+                    } else {
+                        float* o = p.out + ((int64_t)b * p.M + m) * p.T + tq;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) o[i] = norm(lg[i]);
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int t = tq + i;
+                        if (t < p.T) {
+                            float sv = 0.f;                                     // DataCollator pad value
+                            if (t < Tb) { vmax = fmaxf(vmax, lg[i]); vmin = fminf(vmin, lg[i]); sv = norm(lg[i]); }
+                            if (p.out_cl) s_cl[(4 * qq + i) * clp + m] = to_op16(sv);
+                            else p.out[((int64_t)b * p.M + m) * p.T + t] = sv;
+                        }
+                    }
+                }
+            }
+        }
+        vmax = warp_max(vmax);
+        vmin = -warp_max(-vmin);
+        if (lane == 0) { s_red[warp] = vmax; s_red[32 + warp] = vmin; }
+        __syncthreads();                                    // staging tile complete; P / E are free for the next tile
+        if (p.out_cl) {                                     // rows of CP 16-bit values, two per 32-bit word: a warp per frame
+            const int wpr = p.CP >> 1, mw = (p.M + 1) >> 1; // words per row, words that hold real channels
+            for (int fr = warp; fr < FB && t0 + fr < p.T; fr += nwarp) {
+                uint32_t* dst = reinterpret_cast<uint32_t*>(p.out_cl + ((int64_t)b * p.T + t0 + fr) * p.CP);
+                const op16* srow = s_cl + fr * clp;
+                for (int w = lane; w < wpr; w += 32) {
+                    uint32_t v = 0u;                       // channels >= M: zero
+                    if (w < mw) {
+                        v = *reinterpret_cast<const uint32_t*>(srow + 2 * w);
+                        if (2 * w + 1 >= p.M) v &= 0xffffu;
+                    }
+                    dst[w] = v;
+                }
+            }
+        }
+        if (warp == 0) {
+            float v = lane < nwarp ? s_red[lane] : -INFINITY;
+            float u = lane < nwarp ? s_red[32 + lane] : INFINITY;
+            v = warp_max(v);
+            u = -warp_max(-u);
+            if (lane == 0) {                                // back to log10: monotone, so the max of the products is the product of the max
+                if (v > -INFINITY) atomicMax(p.keys + b, f2key(v * 0.30102999566398120f));
+                p.tile_min[tile] = f2key(u);                 // lg2 domain; +inf for a tile without valid frames: never below a floor
+            }
+        }
+    }
+}
+
+// essentials.py:489: log_mel = maximum(log_mel, log_mel.max() - 8.0), applied in the normalised domain.  One block per
+// frame tile of pass 1; a tile whose smallest value already clears the floor (pass 1 left its minimum in tile_min) is
+// skipped without touching memory, and the others only write where something changes.
+__device__ __forceinline__ bool floor_tile_is_clear(const uint32_t* keys, int64_t batch, int tiles_per_utt, int b, int tile, float& floor_s) {
+    floor_s = ((key2f(keys[b]) - 8.0f) + 4.0f) / 4.0f;
+    const float lg2_min = key2f(keys[batch + (int64_t)b * tiles_per_utt + tile]);
+    return fmaf(lg2_min * 0.30102999566398120f, 0.25f, 1.0f) >= floor_s;           // the very expression pass 1 stored
+}
+
+__global__ void logmel_floor_kernel(float* out, const uint32_t* keys, int64_t batch, const int32_t* lengths,
+                                    int64_t n_samples, int hop, int M, int T, int FB, int tiles_per_utt) {
+    const int b = blockIdx.y, tile = blockIdx.x;
+    float floor_s;
+    if (floor_tile_is_clear(keys, batch, tiles_per_utt, b, tile, floor_s)) return;
+    const int Tb = 1 + (int)(clamp_len(lengths, b, n_samples) / hop);
+    const int t0 = tile * FB, nf = min(FB, Tb - t0);
+    float* o = out + (int64_t)b * M * T + t0;
+    for (int i = threadIdx.x; i < M * FB; i += blockDim.x) {
+        const int m = i / FB, f = i - m * FB;
+        if (f < nf) {
+            float* q = o + (int64_t)m * T + f;
+            if (*q < floor_s) *q = floor_s;
         }
     }
 }
 
 // The same floor on the fused path's 16-bit channels-last tensor, in place: rounding is monotone, so
 // max(rn(x), rn(floor)) == rn(max(x, floor)) bit for bit.  One thread per (frame, 8 channels).
-__global__ void logmel_floor_cl_kernel(op16* a, const uint32_t* keys, const int32_t* lengths,
-                                       int64_t n_samples, int hop, int M, int CP, int T) {
-    const int b = blockIdx.y;
-    const int64_t len = clamp_len(lengths, b, n_samples);
-    const int Tb = min(1 + (int)(len / hop), T);
-    const float fls = ((key2f(keys[b]) - 8.0f) + 4.0f) / 4.0f;
+__global__ void logmel_floor_cl_kernel(op16* a, const uint32_t* keys, int64_t batch, const int32_t* lengths,
+                                       int64_t n_samples, int hop, int M, int CP, int T, int FB, int tiles_per_utt) {
+    const int b = blockIdx.y, tile = blockIdx.x;
+    float fls;
+    if (floor_tile_is_clear(keys, batch, tiles_per_utt, b, tile, fls)) return;
+    const int Tb = min(1 + (int)(clamp_len(lengths, b, n_samples) / hop), T);
     const float fl = unpack_op16x2(pack_op16x2(fls, fls)).x;           // the floor, rounded like the values were
     const int cpr = (M + 7) >> 3;                          // 16-byte chunks per row that hold real channels
-    const int64_t total = (int64_t)Tb * cpr;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int t = (int)(i / cpr), c8 = (int)(i - (int64_t)t * cpr);
-        uint4* ptr = reinterpret_cast<uint4*>(a + ((int64_t)b * T + t) * CP + c8 * 8);
+    const int t0 = tile * FB, nf = min(FB, Tb - t0);
+    for (int i = threadIdx.x; i < nf * cpr; i += blockDim.x) {
+        const int f = i / cpr, c8 = i - f * cpr;
+        uint4* ptr = reinterpret_cast<uint4*>(a + ((int64_t)b * T + t0 + f) * CP + c8 * 8);
         uint4 q = *ptr;
         uint32_t* h = reinterpret_cast<uint32_t*>(&q);
         bool changed = false;
@@ -319,7 +463,8 @@ extern "C" int asrb_logmel_plan_create(int n_fft, int hop, int n_mels, const flo
     kmax = (kmax + 3) & ~3;                                // taps padded with zeros to a multiple of 4 (16-byte weight loads)
     std::vector<float> w((size_t)n_mels * kmax, 0.f);
     for (int m = 0; m < n_mels; ++m)
-        for (int i = 0; i < cnt[m]; ++i) w[(size_t)m * kmax + i] = fbank_host[(size_t)(lo[m] + i) * n_mels + m];
+        for (int i = 0; i < cnt[m]; ++i)        // x 1/4 (exact): the kernel's power spectra are |2 X|^2
+            w[(size_t)m * kmax + i] = 0.25f * fbank_host[(size_t)(lo[m] + i) * n_mels + m];
     std::vector<float2> tw((size_t)R * R);
     for (int k1 = 0; k1 < R; ++k1)
         for (int j = 0; j < R; ++j) {
@@ -355,22 +500,33 @@ extern "C" int64_t asrb_logmel_num_frames(const asrb_logmel_plan* pl, int64_t n)
     return pl && n >= 0 ? 1 + n / pl->hop : -1;
 }
 
-extern "C" size_t asrb_logmel_workspace_bytes(const asrb_logmel_plan* pl, int64_t batch, int64_t) {
-    if (!pl || batch < 0) return 0;
-    return align_up(sizeof(uint32_t) * (size_t)(batch > 0 ? batch : 1), 256);
+namespace asrb {
+int logmel_tile_frames(const asrb_logmel_plan* pl) { return pl->n_fft == 400 ? 32 : 16; }
+// keys: [batch] per-utterance maxima, then [batch][tiles] per-tile minima
+size_t logmel_keys_words(const asrb_logmel_plan* pl, int64_t batch, int64_t n_samples) {
+    const int64_t T = 1 + n_samples / pl->hop, FB = logmel_tile_frames(pl);
+    return (size_t)(batch > 0 ? batch : 1) * (size_t)(1 + (T + FB - 1) / FB);
+}
+}  // namespace asrb
+
+extern "C" size_t asrb_logmel_workspace_bytes(const asrb_logmel_plan* pl, int64_t batch, int64_t n_samples) {
+    if (!pl || batch < 0 || n_samples < 0) return 0;
+    return align_up(sizeof(uint32_t) * logmel_keys_words(pl, batch, n_samples), 256);
 }
 
 namespace asrb {
 
-template <int NFFT, int R, int FB>
+template <int NFFT, int R, int FB, int HOP>
 static int launch_logmel(const asrb_logmel_plan* pl, LogmelParams p, int64_t batch, cudaStream_t st) {
-    using C = LogmelCfg<NFFT, R, FB>;
+    using C = LogmelCfg<NFFT, R, FB, HOP>;
     const int span = (FB - 1) * pl->hop + NFFT;
-    size_t smem = sizeof(float) * (2 * ((span + 3) & ~3) + NFFT) + sizeof(float2) * (R * R + C::GROUPS * C::YSTRIDE) +
-                  sizeof(float) * (size_t)pl->n_mels * pl->kmax + sizeof(int) * (2 * pl->n_mels + 1) +
-                  (p.out_cl ? sizeof(op16) * FB * (p.CP + 2) : 0);
+    const size_t pcm_words = ((span + 3) & ~3) + C::GAP * C::QUADS + 4;
+    size_t smem = C::REGION + sizeof(float) * (pcm_words + NFFT) + sizeof(float2) * (R * R) +
+                  sizeof(float) * (size_t)pl->n_mels * pl->kmax + sizeof(int) * (2 * pl->n_mels);
     if (smem > 227 * 1024) return fail(ASRB_E_ARG, "asrb_logmel_f32: hop/n_mels need %zu B of shared memory", smem);
-    auto kern = logmel_kernel<NFFT, R, FB>;
+    if (p.out_cl && sizeof(op16) * FB * (p.CP + 2) > (size_t)C::E_BYTES)
+        return fail(ASRB_E_ARG, "log-mel: channels-last pitch %d does not fit the staging tile", p.CP);
+    auto kern = logmel_kernel<NFFT, R, FB, HOP>;
     ASRB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 1;
     ASRB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, C::THREADS, smem));
@@ -388,31 +544,29 @@ static int launch_logmel(const asrb_logmel_plan* pl, LogmelParams p, int64_t bat
 // Shared by asrb_logmel_f32 and the fused pcm->hidden path: pass 1 only (values + keys).
 int logmel_pass1(const asrb_logmel_plan* pl, const float* pcm, int64_t batch, int64_t n_samples,
                  int64_t stride, const int32_t* lengths, float* out, uint32_t* keys, cudaStream_t st,
-                 op16* out_cl, int CP) {
+                 op16* out_cl, int CP, float* pool_out, int64_t pool_target) {
     LogmelParams p;
     p.out_cl = out_cl; p.CP = CP;
     if (out_cl && (CP < pl->n_mels || (CP & 7))) return fail(ASRB_E_ARG, "log-mel: channels-last pitch %d for %d mels", CP, pl->n_mels);
     p.pcm = pcm; p.stride = stride; p.n_samples = n_samples; p.lengths = lengths;
     p.hop = pl->hop; p.T = (int)(1 + n_samples / pl->hop); p.M = pl->n_mels; p.kmax = pl->kmax;
     p.window = pl->d_window; p.twiddle = pl->d_twiddle; p.mel_lo = pl->d_lo; p.mel_cnt = pl->d_cnt;
-    p.mel_w = pl->d_w; p.out = out; p.keys = keys;
+    p.mel_w = pl->d_w; p.out = out; p.keys = keys; p.tile_min = keys + batch;
+    p.pool_out = pool_target > 0 ? pool_out : nullptr; p.pool_target = pool_target;
     ASRB_CUDA(cudaMemsetAsync(keys, 0, sizeof(uint32_t) * batch, st));
     const double frames = (double)batch * p.T;
     ProfScope ps("logmel_stft_mel", st, frames * 2.5 * pl->n_fft * log2((double)pl->n_fft),
                  4.0 * batch * ((double)n_samples + (double)pl->n_mels * p.T));
-    if (pl->n_fft == 400) return launch_logmel<400, 20, 32>(pl, p, batch, st);
-    return launch_logmel<1024, 32, 16>(pl, p, batch, st);
+    if (pl->n_fft == 400) return pl->hop == 160 ? launch_logmel<400, 20, 32, 160>(pl, p, batch, st) : launch_logmel<400, 20, 32, 0>(pl, p, batch, st);
+    return pl->hop == 160 ? launch_logmel<1024, 32, 16, 160>(pl, p, batch, st) : launch_logmel<1024, 32, 16, 0>(pl, p, batch, st);
 }
 
 // Floor of the fused path (after logmel_pass1 with out_cl).
 int logmel_floor_cl(const asrb_logmel_plan* pl, op16* a, int CP, const uint32_t* keys, const int32_t* lengths,
                     int64_t batch, int64_t n_samples, cudaStream_t st) {
-    const int T = (int)(1 + n_samples / pl->hop);
-    const int64_t per = (int64_t)T * ((pl->n_mels + 7) / 8);
-    int gx = (int)((per + 256 * 4 - 1) / (256 * 4));
-    if (gx < 1) gx = 1;
-    ProfScope ps("logmel_floor", st, 0.0, 4.0 * batch * T * pl->n_mels);
-    logmel_floor_cl_kernel<<<dim3(gx, (unsigned)batch), 256, 0, st>>>(a, keys, lengths, n_samples, pl->hop, pl->n_mels, CP, T);
+    const int T = (int)(1 + n_samples / pl->hop), FB = logmel_tile_frames(pl), tiles = (T + FB - 1) / FB;
+    ProfScope ps("logmel_floor", st, 0.0, 4.0 * batch * tiles);
+    logmel_floor_cl_kernel<<<dim3((unsigned)tiles, (unsigned)batch), 128, 0, st>>>(a, keys, batch, lengths, n_samples, pl->hop, pl->n_mels, CP, T, FB, tiles);
     ASRB_LAUNCH_CHECK();
     return ASRB_OK;
 }
@@ -436,12 +590,9 @@ extern "C" int asrb_logmel_f32(const asrb_logmel_plan* pl, const float* pcm, int
     cudaStream_t st = (cudaStream_t)stream;
     uint32_t* keys = (uint32_t*)ws;
     ASRB_TRY(logmel_pass1(pl, pcm, batch, n_samples, pcm_stride, lengths, out, keys, st));
-    const int T = (int)(1 + n_samples / pl->hop);
-    const int64_t per = (int64_t)pl->n_mels * T;
-    int gx = (int)((per + 256 * 8 - 1) / (256 * 8));
-    if (gx < 1) gx = 1;
-    ProfScope ps("logmel_floor", st, 0.0, 0.0);
-    logmel_floor_kernel<<<dim3(gx, (unsigned)batch), 256, 0, st>>>(out, keys, lengths, n_samples, pl->hop, pl->n_mels, T);
+    const int T = (int)(1 + n_samples / pl->hop), FB = logmel_tile_frames(pl), tiles = (T + FB - 1) / FB;
+    ProfScope ps("logmel_floor", st, 0.0, 4.0 * batch * tiles);
+    logmel_floor_kernel<<<dim3((unsigned)tiles, (unsigned)batch), 256, 0, st>>>(out, keys, batch, lengths, n_samples, pl->hop, pl->n_mels, T, FB, tiles);
     ASRB_LAUNCH_CHECK();
     return ASRB_OK;
 }
