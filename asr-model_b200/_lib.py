@@ -35,6 +35,7 @@ SYMBOLS = {
     "asrb_logmel_workspace_bytes": (_sz, [_vp, _i64, _i64]),
     "asrb_logmel_f32": (_int, [_vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _sz, _vp]),
     "asrb_waveform_pool_f32": (_int, [_vp, _i64, _i64, _i64, _i64, _vp, _vp]),
+    "asrb_logmel_waveform_f32": (_int, [_vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _i64, _vp, _sz, _vp]),
     "asrb_encoder_create": (_int, [C.POINTER(EncoderConfig), _int, C.POINTER(C.c_char_p), _pp,
                                    C.POINTER(_i64), _pp]),
     "asrb_encoder_destroy": (None, [_vp]),

@@ -573,28 +573,43 @@ int logmel_floor_cl(const asrb_logmel_plan* pl, op16* a, int CP, const uint32_t*
 
 }  // namespace asrb
 
-extern "C" int asrb_logmel_f32(const asrb_logmel_plan* pl, const float* pcm, int64_t batch, int64_t n_samples,
-                               int64_t pcm_stride, const int32_t* lengths, float* out,
-                               void* ws, size_t ws_bytes, void* stream) {
-    if (!pl) return fail(ASRB_E_ARG, "asrb_logmel_f32: NULL plan");
+static int logmel_f32_impl(const char* who, const asrb_logmel_plan* pl, const float* pcm, int64_t batch, int64_t n_samples,
+                           int64_t pcm_stride, const int32_t* lengths, float* out, float* pool_out, int64_t pool_target,
+                           void* ws, size_t ws_bytes, void* stream) {
+    if (!pl) return fail(ASRB_E_ARG, "%s: NULL plan", who);
     if (batch < 0 || n_samples < 0 || pcm_stride < n_samples)
-        return fail(ASRB_E_ARG, "asrb_logmel_f32: bad shape batch=%lld n=%lld stride=%lld",
+        return fail(ASRB_E_ARG, "%s: bad shape batch=%lld n=%lld stride=%lld", who,
                     (long long)batch, (long long)n_samples, (long long)pcm_stride);
     if (batch == 0) return ASRB_OK;
-    if (batch > 65535) return fail(ASRB_E_ARG, "asrb_logmel_f32: batch %lld > 65535", (long long)batch);
-    if (!out || (!pcm && n_samples > 0)) return fail(ASRB_E_ARG, "asrb_logmel_f32: NULL tensor");
-    if (1 + n_samples / pl->hop > 0x7fffffff / 2) return fail(ASRB_E_ARG, "asrb_logmel_f32: too many frames");
+    if (batch > 65535) return fail(ASRB_E_ARG, "%s: batch %lld > 65535", who, (long long)batch);
+    if (!out || (!pcm && n_samples > 0)) return fail(ASRB_E_ARG, "%s: NULL tensor", who);
+    if (1 + n_samples / pl->hop > 0x7fffffff / 2) return fail(ASRB_E_ARG, "%s: too many frames", who);
+    if (pool_target > 0 && (!pool_out || pool_target >= n_samples || pool_target > 1 + n_samples / pl->hop))
+        return fail(ASRB_E_ARG, "%s: pooled target %lld needs an output, target < samples and target <= frames", who, (long long)pool_target);
     if (!ws || ws_bytes < asrb_logmel_workspace_bytes(pl, batch, n_samples) || ((uintptr_t)ws & 3))
-        return fail(ASRB_E_WORKSPACE, "asrb_logmel_f32: workspace too small or NULL (%zu B given)", ws_bytes);
+        return fail(ASRB_E_WORKSPACE, "%s: workspace too small or NULL (%zu B given)", who, ws_bytes);
     ASRB_TRY(require_sm100());
     cudaStream_t st = (cudaStream_t)stream;
     uint32_t* keys = (uint32_t*)ws;
-    ASRB_TRY(logmel_pass1(pl, pcm, batch, n_samples, pcm_stride, lengths, out, keys, st));
+    ASRB_TRY(logmel_pass1(pl, pcm, batch, n_samples, pcm_stride, lengths, out, keys, st, nullptr, 0, pool_out, pool_target));
     const int T = (int)(1 + n_samples / pl->hop), FB = logmel_tile_frames(pl), tiles = (T + FB - 1) / FB;
     ProfScope ps("logmel_floor", st, 0.0, 4.0 * batch * tiles);
     logmel_floor_kernel<<<dim3((unsigned)tiles, (unsigned)batch), 256, 0, st>>>(out, keys, batch, lengths, n_samples, pl->hop, pl->n_mels, T, FB, tiles);
     ASRB_LAUNCH_CHECK();
     return ASRB_OK;
+}
+
+extern "C" int asrb_logmel_f32(const asrb_logmel_plan* pl, const float* pcm, int64_t batch, int64_t n_samples,
+                               int64_t pcm_stride, const int32_t* lengths, float* out,
+                               void* ws, size_t ws_bytes, void* stream) {
+    return logmel_f32_impl("asrb_logmel_f32", pl, pcm, batch, n_samples, pcm_stride, lengths, out, nullptr, 0, ws, ws_bytes, stream);
+}
+
+extern "C" int asrb_logmel_waveform_f32(const asrb_logmel_plan* pl, const float* pcm, int64_t batch, int64_t n_samples,
+                                        int64_t pcm_stride, const int32_t* lengths, float* out, float* pool_out,
+                                        int64_t pool_target, void* ws, size_t ws_bytes, void* stream) {
+    return logmel_f32_impl("asrb_logmel_waveform_f32", pl, pcm, batch, n_samples, pcm_stride, lengths, out, pool_out, pool_target,
+                           ws, ws_bytes, stream);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -617,6 +632,22 @@ __global__ void waveform_pool_kernel(const float* __restrict__ pcm, int64_t stri
     acc = warp_sum(acc);
     if (lane == 0) out[w] = acc / (float)(e - s);
 }
+// target >= n: F.interpolate(mode="linear", align_corners=False) (essentials.py:505-506): source position
+// (i + 0.5) n / target - 0.5 clamped at 0, two taps, weights (1 - l, l) -- the arithmetic of ATen's upsample_linear1d.
+__global__ void waveform_interp_kernel(const float* __restrict__ pcm, int64_t stride, int64_t n, int64_t target,
+                                       float* __restrict__ out, int64_t total) {
+    const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= total) return;
+    const int64_t b = w / target, i = w - b * target;
+    const float scale = (float)n / (float)target;
+    float src = scale * ((float)i + 0.5f) - 0.5f;
+    src = src < 0.f ? 0.f : src;
+    const int64_t i0 = (int64_t)src;
+    const int64_t i1 = i0 + (i0 < n - 1 ? 1 : 0);
+    const float l1 = src - (float)i0, l0 = 1.0f - l1;
+    const float* x = pcm + b * stride;
+    out[w] = l0 * x[i0] + l1 * x[i1];
+}
 }  // namespace asrb
 
 extern "C" int asrb_waveform_pool_f32(const float* pcm, int64_t batch, int64_t n_samples, int64_t pcm_stride,
@@ -625,12 +656,16 @@ extern "C" int asrb_waveform_pool_f32(const float* pcm, int64_t batch, int64_t n
         return fail(ASRB_E_ARG, "asrb_waveform_pool_f32: bad shape");
     if (batch == 0 || target == 0) return ASRB_OK;
     if (!pcm || !out) return fail(ASRB_E_ARG, "asrb_waveform_pool_f32: NULL tensor");
-    if (target >= n_samples)
-        return fail(ASRB_E_ARG, "asrb_waveform_pool_f32: target %lld >= %lld samples (the reference interpolates there; unsupported)",
-                    (long long)target, (long long)n_samples);
+    if (n_samples == 0) return fail(ASRB_E_ARG, "asrb_waveform_pool_f32: empty input");
     ASRB_TRY(require_sm100());
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t total = batch * target;
+    if (target >= n_samples) {                              // the reference's `else` branch: linear interpolation
+        ProfScope ps("waveform_interp", st, 0.0, 4.0 * batch * ((double)n_samples + target));
+        waveform_interp_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(pcm, pcm_stride, n_samples, target, out, total);
+        ASRB_LAUNCH_CHECK();
+        return ASRB_OK;
+    }
     ProfScope ps("waveform_pool", st, 0.0, 4.0 * batch * ((double)n_samples + target));
     const int64_t blocks = (total * 32 + 255) / 256;
     if (blocks > 0x7fffffff) return fail(ASRB_E_ARG, "asrb_waveform_pool_f32: too large");

@@ -72,7 +72,12 @@ class AudioEncoder(nn.Module):
 
     # ------------------------------------------------------------------ weights -> handle
     def _weights_version(self):
-        return sum(int(t._version) for t in self.state_dict().values())
+        """Sum of the in-place version counters of every parameter and buffer (cached list: no state_dict() per forward)."""
+        ts = self.__dict__.get("_vt")
+        if ts is None:
+            ts = [t for t in list(self.parameters()) + list(self.buffers())]
+            self.__dict__["_vt"] = ts
+        return sum(int(t._version) for t in ts)
 
     def prepare(self, device=None):
         """Fold weight-norm / BatchNorm, pack and upload the weights (done lazily by forward;
@@ -108,8 +113,13 @@ class AudioEncoder(nn.Module):
         except Exception:
             pass
 
+    def _apply(self, fn, *a, **kw):                     # .to() / .cuda() may replace parameter tensors: drop the cached list
+        self.__dict__.pop("_vt", None)
+        return super()._apply(fn, *a, **kw)
+
     def load_state_dict(self, state_dict, strict=True, assign=False):
         r = super().load_state_dict(state_dict, strict=strict, assign=assign)
+        self.__dict__.pop("_vt", None)
         if self._handles:
             self._release()
         return r
@@ -201,8 +211,8 @@ class AudioEncoder(nn.Module):
         elif tuple(out.shape) != (B, T, self.dims) or out.dtype != self.out_dtype or not out.is_contiguous():
             raise ValueError("out must be a contiguous [B, T, dims] tensor of the module's out_dtype")
         mel = torch.empty(B, self.mels, T, device=wave.device, dtype=torch.float32) if return_logmel else None
-        if lengths is not None:
-            lengths = lengths.to(wave.device, torch.int32).contiguous()
+        from .frontend import check_lengths
+        lengths = check_lengths(lengths, B, N, wave.device)
         need = self._lib.asrb_pcm_to_hidden_workspace_bytes(frontend.handle, h, B, N)
         ws = self._workspace(wave.device, need)
         with torch.cuda.device(wave.device):

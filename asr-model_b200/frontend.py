@@ -40,6 +40,26 @@ def _fbank(n_freqs: int, n_mels: int, sample_rate: int, f_min: float, f_max: flo
     return torch.max(torch.zeros(1), torch.min(down, up)).contiguous()
 
 
+def check_lengths(lengths: Optional[torch.Tensor], batch: int, n_samples: int, device) -> Optional[torch.Tensor]:
+    """``lengths`` -> int32 ``[batch]`` on ``device``.  A host tensor is validated here (0 <= len <= n_samples) before
+    upload; a device tensor is not synchronised on -- the kernels clamp every length to [0, n_samples] themselves."""
+    if lengths is None:
+        return None
+    lengths = torch.as_tensor(lengths)
+    if lengths.numel() != batch:
+        raise ValueError(f"lengths has {lengths.numel()} entries for a batch of {batch}")
+    if not lengths.is_cuda and lengths.numel() and (int(lengths.min()) < 0 or int(lengths.max()) > n_samples):
+        raise ValueError(f"lengths must lie in [0, {n_samples}]")
+    return lengths.to(device, torch.int32).contiguous()
+
+
+def pooled_target(n_samples: int, hop_length: int = HOP, sample_rate: int = SAMPLE_RATE) -> int:
+    """Length of the reference's ``waveform`` feature, in Python floats exactly as written there
+    (essentials.py:495: e.g. N = 4640 gives 28, not 29)."""
+    assert sample_rate % hop_length == 0                     # exact_div, essentials.py:296-298
+    return int((n_samples / sample_rate) * (sample_rate // hop_length))
+
+
 class LogMel:
     """A front-end plan: window + banded filterbank resident on one GPU."""
 
@@ -74,8 +94,10 @@ class LogMel:
         return 1 + n_samples // self.hop
 
     def __call__(self, wave: torch.Tensor, lengths: Optional[torch.Tensor] = None,
-                 out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """``wave [B, N]`` (or ``[N]``) fp32 on the plan's GPU -> ``[B, n_mels, 1 + N//hop]``."""
+                 out: Optional[torch.Tensor] = None, pooled_target: int = 0):
+        """``wave [B, N]`` (or ``[N]``) fp32 on the plan's GPU -> ``[B, n_mels, 1 + N//hop]``.
+        ``pooled_target > 0``: the same pass also emits the average-pooled ``waveform`` feature ``[B, 1, target]``
+        (essentials.py:493-503) and the call returns ``(log_mel, waveform)``."""
         squeeze = wave.dim() == 1
         if squeeze:
             wave = wave.unsqueeze(0)
@@ -90,17 +112,26 @@ class LogMel:
         T = self.num_frames(N)
         if out is None:
             out = torch.empty(B, self.n_mels, T, device=wave.device, dtype=torch.float32)
-        if lengths is not None:
-            lengths = lengths.to(wave.device, torch.int32).contiguous()
+        lengths = check_lengths(lengths, B, N, wave.device)
         need = self.lib.asrb_logmel_workspace_bytes(self._plan, B, N)
         if self._ws is None or self._ws.numel() < need or self._ws.device != wave.device:
             self._ws = torch.empty(max(need, 256), device=wave.device, dtype=torch.uint8)
+        pooled = torch.empty(B, 1, pooled_target, device=wave.device, dtype=torch.float32) if pooled_target > 0 else None
         with torch.cuda.device(wave.device):
-            _lib.check(self.lib.asrb_logmel_f32(
-                self._plan, wave.data_ptr(), B, N, wave.stride(0) if B > 1 else max(N, 1),
-                lengths.data_ptr() if lengths is not None else None,
-                out.data_ptr(), self._ws.data_ptr(), self._ws.numel(), _lib.stream_ptr()),
-                "asrb_logmel_f32")
+            if pooled is None:
+                _lib.check(self.lib.asrb_logmel_f32(
+                    self._plan, wave.data_ptr(), B, N, wave.stride(0) if B > 1 else max(N, 1),
+                    lengths.data_ptr() if lengths is not None else None,
+                    out.data_ptr(), self._ws.data_ptr(), self._ws.numel(), _lib.stream_ptr()),
+                    "asrb_logmel_f32")
+            else:
+                _lib.check(self.lib.asrb_logmel_waveform_f32(
+                    self._plan, wave.data_ptr(), B, N, wave.stride(0) if B > 1 else max(N, 1),
+                    lengths.data_ptr() if lengths is not None else None,
+                    out.data_ptr(), pooled.data_ptr(), pooled_target, self._ws.data_ptr(), self._ws.numel(),
+                    _lib.stream_ptr()), "asrb_logmel_waveform_f32")
+        if pooled is not None:
+            return (out[0], pooled[0]) if squeeze else (out, pooled)
         return out[0] if squeeze else out
 
 
@@ -137,8 +168,7 @@ def waveform_feature(wave: torch.Tensor, hop_length: int = HOP, sample_rate: int
     if wave.stride(-1) != 1:
         wave = wave.contiguous()
     B, N = wave.shape
-    assert sample_rate % hop_length == 0                     # exact_div, essentials.py:296-298
-    target = int((N / sample_rate) * (sample_rate // hop_length))
+    target = pooled_target(N, hop_length, sample_rate)
     out = torch.empty(B, 1, target, device=wave.device, dtype=torch.float32)
     with torch.cuda.device(wave.device):
         _lib.check(lib.asrb_waveform_pool_f32(wave.data_ptr(), B, N, wave.stride(0) if B > 1 else max(N, 1), target,
@@ -156,15 +186,40 @@ def extract_features(batch, tokenizer=None, spectrogram=False, pitch=False, wave
         raise NotImplementedError("only spectrogram=True / waveform=True are on the accelerated path")
     labels = tokenizer.encode(batch["transcription" if "transcription" in batch else "sentence"]) \
         if tokenizer is not None else None
-    audio = batch["audio"]
-    if isinstance(audio, dict):                                   # load_wave dict branch, essentials.py:314-316
-        wave = torch.as_tensor(audio["array"]).float()
-    elif torch.is_tensor(audio):
-        wave = audio.float()
-    else:
-        raise TypeError("Invalid wave_data format.")            # essentials.py:318
+    wave, sample_rate_in = load_wave(batch["audio"], sample_rate)
     wave = wave.to(device)
-    s_tensor = log_mel(wave, mels, n_fft, hop_length, sample_rate) if spectrogram else None
-    w_tensor = waveform_feature(wave, hop_length, sample_rate) if waveform else None       # [1, target]
+    target = pooled_target(wave.shape[-1], hop_length, sample_rate) if waveform else 0
+    if spectrogram and waveform and wave.dim() == 1 and 0 < target < wave.shape[-1] and target <= 1 + wave.shape[-1] // hop_length:
+        # one pass over the PCM for both features (asrb_logmel_waveform_f32)
+        s_tensor, w_tensor = _plan_for(mels, n_fft, hop_length, sample_rate, wave.device)(wave, pooled_target=target)
+    else:
+        s_tensor = log_mel(wave, mels, n_fft, hop_length, sample_rate) if spectrogram else None
+        w_tensor = waveform_feature(wave, hop_length, sample_rate) if waveform else None       # [1, target]
     return {"waveform": w_tensor, "spectrogram": s_tensor, "pitch_tokens": None, "pitch": None,
             "harmonic": None, "aperiodic": None, "labels": labels, "phase": None}
+
+
+def load_wave(audio, sample_rate: int = SAMPLE_RATE):
+    """``load_wave`` of the reference (essentials.py:301-319): a ``str`` path is read with ``soundfile`` as float32 and
+    PEAK-NORMALISED (mono: ``wp / max|wp|``; multi-channel: per-channel ``wp / wp.max(axis=0)`` when any maximum is
+    positive, then transposed to ``[channels, N]``); a dict (the datasets ``audio`` column) is taken as it is; a tensor is
+    accepted as a convenience.  Returns ``(waveform fp32, sample_rate)``.  Host-side glue, not on the timed path."""
+    if isinstance(audio, str):
+        try:
+            import soundfile as sf
+        except ImportError as e:
+            raise ImportError("extract_features was given a file path: reading it needs the `soundfile` package, "
+                              "exactly as the reference's load_wave does (essentials.py:302-303)") from e
+        wp, sample_rate = sf.read(audio, dtype="float32")
+        if wp.ndim > 1:
+            abs_max = wp.max(axis=0)                                        # essentials.py:306 (max, not max-abs, as written there)
+            wp = wp / abs_max if any(abs_max > 0) else wp
+            return torch.from_numpy(wp.T.copy()), sample_rate
+        abs_max = max(abs(wp)) if len(wp) else 0.0
+        wp = wp / abs_max if abs_max > 0 else wp
+        return torch.from_numpy(wp), sample_rate
+    if isinstance(audio, dict):                                             # essentials.py:314-316
+        return torch.as_tensor(audio["array"]).float(), audio.get("sampling_rate", sample_rate)
+    if torch.is_tensor(audio):
+        return audio.float(), sample_rate
+    raise TypeError("Invalid wave_data format.")                           # essentials.py:318

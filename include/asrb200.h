@@ -87,13 +87,22 @@ int asrb_logmel_f32(const asrb_logmel_plan* plan,
                     float* out,
                     void* workspace, size_t workspace_bytes, void* stream);
 
-/* The `waveform` feature of extract_features (essentials.py:493-503): PCM resampled to the frame
- * rate with adaptive average pooling, out[b][i] = mean(pcm[b][floor(i n/target) : ceil((i+1) n/target))).
+/* The `waveform` feature of extract_features (essentials.py:493-510): PCM resampled to the frame
+ * rate.  n_samples > target: adaptive average pooling, out[b][i] = mean(pcm[b][floor(i n/target) : ceil((i+1) n/target)))
+ * (essentials.py:503); otherwise F.interpolate(mode="linear", align_corners=False) (essentials.py:505-506).
  * `target` is computed by the binding exactly as the reference does
- * (int((n / sample_rate) * (sample_rate // hop))).  pcm [batch][pcm_stride], out [batch][target] fp32 device.
- * target < n_samples (the reference's linear-interpolation branch for shorter inputs is not built). */
+ * (int((n / sample_rate) * (sample_rate // hop))).  pcm [batch][pcm_stride], out [batch][target] fp32 device. */
 int asrb_waveform_pool_f32(const float* pcm, int64_t batch, int64_t n_samples, int64_t pcm_stride,
                            int64_t target, float* out, void* stream);
+
+/* extract_features(spectrogram=True, waveform=True) in ONE pass over the PCM: asrb_logmel_f32 plus the average-pooled
+ * waveform feature taken from the samples the front-end kernel has staged in shared memory anyway.
+ * pool_out [batch][pool_target] fp32 device; 0 < pool_target < n_samples and pool_target <= frames (the pooling branch:
+ * essentials.py:502-503); results equal asrb_logmel_f32 + asrb_waveform_pool_f32 bit for bit.  pool_target = 0: no pooling. */
+int asrb_logmel_waveform_f32(const asrb_logmel_plan* plan,
+                             const float* pcm, int64_t batch, int64_t n_samples, int64_t pcm_stride,
+                             const int32_t* lengths, float* out, float* pool_out, int64_t pool_target,
+                             void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Encoder.  Replaces AudioEncoder.__init__/forward (model.py:120-169) with norm=False:

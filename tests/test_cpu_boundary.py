@@ -94,3 +94,29 @@ def test_extract_features_signature_matches_reference():
         extract_features({"audio": {"array": [0.0]}, "transcription": "x"}, None, pitch=True)
     with pytest.raises(TypeError):
         extract_features({"audio": 3, "transcription": "x"}, None, spectrogram=True)
+
+
+def test_load_wave_follows_the_reference(monkeypatch):
+    """essentials.py:301-319: str path -> soundfile read + peak normalisation; dict -> as is; anything else -> TypeError."""
+    import sys
+    import types
+    import numpy as np
+    import torch
+    from asr_model_b200.frontend import load_wave
+    fake = types.ModuleType("soundfile")
+    mono = np.array([0.1, -0.5, 0.25], dtype=np.float32)
+    stereo = np.array([[0.1, -0.2], [0.4, 0.1], [-0.8, 0.05]], dtype=np.float32)
+    fake.read = lambda path, dtype="float32": ((mono if "mono" in path else stereo).copy(), 16000)
+    monkeypatch.setitem(sys.modules, "soundfile", fake)
+    w, sr = load_wave("mono.wav")
+    assert sr == 16000 and torch.equal(w, torch.from_numpy(mono / np.float32(0.5)))
+    w2, _ = load_wave("stereo.wav")                       # per-channel max (not max-abs), transposed: as the reference writes it
+    assert w2.shape == (2, 3) and torch.equal(w2, torch.from_numpy((stereo / stereo.max(axis=0)).T.copy()))
+    d, sr = load_wave({"array": mono, "sampling_rate": 8000})
+    assert sr == 8000 and torch.equal(d, torch.from_numpy(mono))        # no normalisation on the dict branch
+    import pytest
+    with pytest.raises(TypeError):
+        load_wave(3.14)
+    monkeypatch.setitem(sys.modules, "soundfile", None)
+    with pytest.raises(ImportError):
+        load_wave("x.wav")

@@ -133,3 +133,52 @@ def test_waveform_feature_matches_reference(ab, golden):
     h = m(r["waveform"]).cpu()
     ref_h = oracle.audio_encoder_forward(sd, oracle.waveform_feature(waves[0]), 4)
     assert float((h - ref_h).abs().max()) <= 1e-4
+
+
+def test_fused_spectrogram_and_waveform_pass_equals_separate_calls(ab):
+    """the average-pooled waveform feature comes out of the front-end kernel's own pass over the PCM
+    (asrb_logmel_waveform_f32), bit-equal to the two separate calls -- also when the clip length is not a multiple of the
+    hop and pooling bins drift away from the staged span."""
+    from asr_model_b200.frontend import LogMel, pooled_target
+    for n_fft, n in ((400, 48000), (400, 4640 * 7 + 3), (1024, 16000 + 37), (400, 480000)):
+        waves = synth.make_batch("WH2", n).cuda()
+        fe = LogMel(80, n_fft)
+        tg = pooled_target(n)
+        mel, pooled = fe(waves, pooled_target=tg)
+        assert pooled.shape == (3, 1, tg)
+        assert torch.equal(mel, fe(waves))
+        assert torch.equal(pooled, ab.waveform_feature(waves)), (n_fft, n)
+        for b in range(3):
+            assert float((pooled[b].cpu() - oracle.waveform_feature(waves[b].cpu())).abs().max()) <= 1e-6
+
+
+def test_waveform_interpolation_branch_matches_reference_op(ab):
+    """essentials.py:505-506: when the clip is not longer than the target (hop 1) the reference interpolates linearly."""
+    for n in (5, 16, 999, 16000):
+        w = synth.make_wave("W", n)
+        ref = oracle.waveform_feature(w, sample_rate=16000, hop=1)           # target = n * 16000 / 16000 ... = n: current <= target
+        out = ab.waveform_feature(w.cuda(), hop_length=1).cpu()
+        assert out.shape == ref.shape and float((out - ref).abs().max()) <= 1e-6, n
+    x = torch.arange(8, dtype=torch.float32)
+    lib = ab.lib.load()
+    out = torch.empty(1, 20, device="cuda")
+    ab.lib.check(lib.asrb_waveform_pool_f32(x.cuda().data_ptr(), 1, 8, 8, 20, out.data_ptr(), None), "asrb_waveform_pool_f32")
+    ref = torch.nn.functional.interpolate(x.view(1, 1, -1), size=20, mode="linear", align_corners=False).view(1, 20)
+    assert float((out.cpu() - ref).abs().max()) <= 1e-6
+
+
+def test_bad_lengths_are_rejected_on_the_host_and_clamped_on_the_device(ab):
+    from asr_model_b200.frontend import LogMel
+    waves = synth.make_batch("WH", 8000).cuda()
+    fe = LogMel(80, 400)
+    with pytest.raises(ValueError):
+        fe(waves, lengths=torch.tensor([8000, 8001]))
+    with pytest.raises(ValueError):
+        fe(waves, lengths=torch.tensor([-1, 5]))
+    # a device tensor is not synchronised on: the kernels clamp, so an oversized length behaves like the full clip and
+    # nothing is written past the tensor (guard rows stay untouched)
+    buf = torch.full((4, 80, fe.num_frames(8000)), 7.0, device="cuda")
+    fe(waves, lengths=torch.tensor([10 ** 6, -5], device="cuda"), out=buf[1:3])
+    assert torch.all(buf[0] == 7.0) and torch.all(buf[3] == 7.0)
+    ref = oracle.log_mel_batch(waves.cpu(), 80, 400, lengths=[8000, 0])
+    assert float((buf[1:3].cpu() - ref).abs().max()) <= TOL
