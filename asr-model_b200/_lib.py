@@ -41,9 +41,11 @@ SYMBOLS = {
     "asrb_encoder_destroy": (None, [_vp]),
     "asrb_encoder_workspace_bytes": (_sz, [_vp, _i64, _i64]),
     "asrb_encoder_forward": (_int, [_vp, _vp, _i64, _i32, _i64, _vp, _int, _vp, _sz, _vp]),
+    "asrb_encoder_forward_ragged": (_int, [_vp, _vp, _i64, _i32, _i64, _vp, _vp, _int, _vp, _sz, _vp]),
     "asrb_encoder_forward_streams": (_int, [_vp, _i32, _pp, C.POINTER(_i32), _i64, _i64, _vp, _int, _vp, _sz, _vp]),
     "asrb_pcm_to_hidden_workspace_bytes": (_sz, [_vp, _vp, _i64, _i64]),
     "asrb_pcm_to_hidden": (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _int, _vp, _sz, _vp]),
+    "asrb_pcm_to_hidden_ragged": (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _int, _vp, _sz, _vp]),
     "asrb_attention_create": (_int, [_i32, _i32, _int, _int, C.POINTER(C.c_char_p), _pp,
                                      C.POINTER(_i64), _pp]),
     "asrb_attention_destroy": (None, [_vp]),

@@ -81,6 +81,7 @@ struct TcGemmArgs {
     const float* pos;            // optional [T][Nout] sinusoid table added after dw_act
     int out_f32;                 // store fp32 (consumer is a depthwise conv, not an MMA); not with TC_LN
     int out_bf16;                // store bf16: this launch writes the hidden states the caller receives
+    const int32_t* frames_eff;   // ragged batches: [B] device, frames per utterance still needed downstream (tiles past it are skipped), or NULL
 };
 bool tc_gemm_supported(int K, int N, int epilogue);
 int  tc_glu_tile_n(int N);                    // BN the GLU weight interleave must use

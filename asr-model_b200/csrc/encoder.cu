@@ -220,6 +220,7 @@ namespace {
 
 struct EncBuffers {                    // carved from the caller's workspace
     void* a0; void* X; void* Y; void* G; void* U; void* H; void* wide; void* ffn; float* pos;
+    int32_t* frames_valid; int32_t* frames_eff;
     bool ok;
 };
 
@@ -236,6 +237,7 @@ size_t enc_ws_bytes(const asrb_encoder* e, int64_t B, int64_t T) {
     add(rows * wide * es);                                                  // qkv | fp32 GLU input
     add(e->cfg.enc ? rows * e->cfg.ffn * es : 0);                           // FFN hidden
     add((size_t)T * D * 4);                                                 // sinusoid table
+    add((size_t)B * 4); add((size_t)B * 4);                                 // ragged batches: valid / still-needed frames per utterance
     return align_up(n, 256) + 256;
 }
 
@@ -251,6 +253,7 @@ EncBuffers carve(const asrb_encoder* e, int64_t B, int64_t T, void* ws, size_t w
     b.wide = a.take<char>(rows * wide * es);
     b.ffn = a.take<char>(e->cfg.enc ? rows * e->cfg.ffn * es : 0);
     b.pos = a.take<float>((size_t)T * D);
+    b.frames_valid = a.take<int32_t>((size_t)B); b.frames_eff = a.take<int32_t>((size_t)B);
     b.ok = a.ok();
     return b;
 }
@@ -261,12 +264,37 @@ __global__ void convert_kernel(const TI* __restrict__ in, TO* __restrict__ out, 
         io<TO>::st(out + i, io<TI>::ld(in + i));
 }
 
+// Ragged batches (DataCollator pads to the longest clip, essentials.py:555-572).  valid[b] = frames of
+// utterance b that hold audio; eff[b] = frames some valid output frame still depends on: every conv block widens the cone
+// by 1 (k3) + 7 (depthwise-15) + 1 (depthwise-3) frames, the stem by 1.
+__global__ void ragged_extents_kernel(const int32_t* __restrict__ lengths, int from_samples, int64_t n_samples, int hop, int T,
+                                      int halo, int32_t* __restrict__ valid, int32_t* __restrict__ eff, int B) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    int64_t v = lengths[b];
+    if (from_samples) { v = v < 0 ? 0 : (v > n_samples ? n_samples : v); v = 1 + v / hop; }
+    v = v < 0 ? 0 : (v > T ? T : v);
+    valid[b] = (int)v;
+    eff[b] = (int)(v + halo > T ? T : v + halo);
+}
+// rows t >= valid[b] of out [B][T][D] <- 0 (16-byte stores; D * element size is a multiple of 16)
+__global__ void zero_tail_kernel(uint4* __restrict__ out, const int32_t* __restrict__ valid, int T, int row_vec) {
+    const int b = blockIdx.y;
+    const int v = valid[b];
+    const int64_t n = (int64_t)(T - v) * row_vec;
+    uint4* o = out + ((int64_t)b * T + v) * row_vec;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        o[i] = make_uint4(0u, 0u, 0u, 0u);
+}
+
 // GEMM + LayerNorm on the tensor cores: fused epilogue when the row fits TMEM (N <= 512), else
 // GEMM(+residual) to bf16 followed by the row kernel.
 int tc_gemm_ln(const op16* A, const op16* W, const float* bias, const op16* res,
                const float* gamma, const float* beta, void* out, void* tmp, int64_t B, int64_t T, int K, int N,
-               int taps, cudaStream_t st, const float* res32 = nullptr, float* out32 = nullptr, int out_bf16 = 0) {
+               int taps, cudaStream_t st, const float* res32 = nullptr, float* out32 = nullptr, int out_bf16 = 0,
+               const int32_t* frames_eff = nullptr) {
     TcGemmArgs g{};
+    g.frames_eff = frames_eff;
     g.A = A; g.W = W; g.bias = bias; g.res = res; g.gamma = gamma; g.beta = beta;
     g.B = B; g.T = T; g.K = K; g.N = N; g.taps = taps; g.act = ACT_NONE; g.eps = 1e-5f;
     if (tc_gemm_supported(K, N, TC_LN)) {
@@ -280,7 +308,8 @@ int tc_gemm_ln(const op16* A, const op16* W, const float* bias, const op16* res,
 
 // Stem of one feature stream: conv1 (mels -> D, k3; its input is already in w.a0) or conv2 (1 -> D, k3, straight
 // from x), model.py:152-155, + layer 0's leading activation, written to X (B x T rows).
-int encoder_stem(asrb_encoder* e, const EncBuffers& w, const float* x_c1, int in_ch, int64_t B, int64_t T, void* X, cudaStream_t st) {
+int encoder_stem(asrb_encoder* e, const EncBuffers& w, const float* x_c1, int in_ch, int64_t B, int64_t T, void* X, cudaStream_t st,
+                 const int32_t* frames_eff = nullptr) {
     const int D = e->cfg.dims;
     const bool bf = e->cfg.compute == ASRB_BF16;
     const DType dt = bf ? DT_OP16 : DT_F32;
@@ -293,22 +322,47 @@ int encoder_stem(asrb_encoder* e, const EncBuffers& w, const float* x_c1, int in
         TcGemmArgs g{};
         g.A = (const op16*)w.a0; g.W = e->stem1_h; g.bias = e->stem1_b; g.out = X;
         g.B = B; g.T = T; g.K = e->CP; g.N = D; g.taps = 3; g.epilogue = TC_BIAS_ACT; g.act = stem_act;
+        g.frames_eff = frames_eff;
         return launch_gemm_tc(g, st);
     }
     return launch_gemm_simt(w.a0, DT_F32, e->stem1_f, e->stem1_b, nullptr, X, DT_F32, B, T, e->cfg.mels, D, 3, stem_act, st);
 }
 
-int encoder_layers(asrb_encoder* e, const EncBuffers& w, int64_t B, int64_t T, void* out, int out_dtype, cudaStream_t st);
+int encoder_layers(asrb_encoder* e, const EncBuffers& w, int64_t B, int64_t T, void* out, int out_dtype, cudaStream_t st,
+                   const int32_t* frames_eff = nullptr);
 
 // Everything after the stem input is in place (a0 for in_ch == mels, x itself for in_ch == 1).
 int encoder_body(asrb_encoder* e, const EncBuffers& w, const float* x_c1, int in_ch, int64_t B, int64_t T,
-                 void* out, int out_dtype, cudaStream_t st) {
-    ASRB_TRY(encoder_stem(e, w, x_c1, in_ch, B, T, w.X, st));
-    return encoder_layers(e, w, B, T, out, out_dtype, st);
+                 void* out, int out_dtype, cudaStream_t st, const int32_t* frames_eff = nullptr) {
+    ASRB_TRY(encoder_stem(e, w, x_c1, in_ch, B, T, w.X, st, in_ch == 1 ? nullptr : frames_eff));
+    return encoder_layers(e, w, B, T, out, out_dtype, st, frames_eff);
+}
+
+// Can padded tiles be skipped without changing any valid output frame?  Only in the conv stack on the tensor-core path: the
+// TransformerEncoderLayer attends over every frame without a mask (model.py:163), so there the padding is part of the result.
+bool can_skip_padding(const asrb_encoder* e) { return e->cfg.compute == ASRB_BF16 && !e->cfg.enc; }
+
+// lengths -> (valid, eff) on the device; returns the array to hand to the kernels (NULL: compute everything)
+int ragged_prepare(const asrb_encoder* e, const EncBuffers& w, const int32_t* lengths, bool from_samples, int64_t n_samples, int hop,
+                   int64_t B, int64_t T, cudaStream_t st, const int32_t** frames_eff) {
+    const int halo = 9 * e->cfg.layer + 1;
+    ragged_extents_kernel<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(lengths, from_samples ? 1 : 0, n_samples, hop, (int)T, halo,
+                                                                       w.frames_valid, w.frames_eff, (int)B);
+    ASRB_LAUNCH_CHECK();
+    *frames_eff = can_skip_padding(e) ? w.frames_eff : nullptr;
+    return ASRB_OK;
+}
+int ragged_finish(const asrb_encoder* e, const EncBuffers& w, void* out, int out_dtype, int64_t B, int64_t T, cudaStream_t st) {
+    const int row_vec = e->cfg.dims * (out_dtype == ASRB_BF16 ? 2 : 4) / 16;
+    ProfScope ps("zero_padded_rows", st, 0.0, 0.0);
+    zero_tail_kernel<<<dim3(64, (unsigned)B), 256, 0, st>>>((uint4*)out, w.frames_valid, (int)T, row_vec);
+    ASRB_LAUNCH_CHECK();
+    return ASRB_OK;
 }
 
 // The layer stack (and the optional TransformerEncoderLayer) over B x T rows whose stem output sits in w.X.
-int encoder_layers(asrb_encoder* e, const EncBuffers& w, int64_t B, int64_t T, void* out, int out_dtype, cudaStream_t st) {
+int encoder_layers(asrb_encoder* e, const EncBuffers& w, int64_t B, int64_t T, void* out, int out_dtype, cudaStream_t st,
+                   const int32_t* frames_eff) {
     const int D = e->cfg.dims, L = e->cfg.layer;
     const bool bf = e->cfg.compute == ASRB_BF16;
     const DType dt = bf ? DT_OP16 : DT_F32;
@@ -322,12 +376,13 @@ int encoder_layers(asrb_encoder* e, const EncBuffers& w, int64_t B, int64_t T, v
         const LayerW& lw = e->layers[i];
         const bool last = i == L - 1;
         if (bf) {
-            ASRB_TRY(tc_gemm_ln((const op16*)w.X, lw.wc_h, lw.bc, nullptr, lw.gamma, lw.beta, w.Y, w.H, B, T, D, D, 3, st));
+            ASRB_TRY(tc_gemm_ln((const op16*)w.X, lw.wc_h, lw.bc, nullptr, lw.gamma, lw.beta, w.Y, w.H, B, T, D, D, 3, st,
+                                nullptr, nullptr, 0, frames_eff));
             // point1 + GLU + depthwise-15 (BatchNorm folded) + SiLU in one kernel: Y -> U
             TcGemmArgs g{};
             g.A = (const op16*)w.Y; g.W = lw.w1_h; g.bias = lw.b1_glu; g.out = w.U;
             g.B = B; g.T = T; g.K = D; g.N = 2 * D; g.taps = 1; g.epilogue = TC_GLU_DW; g.act = ACT_NONE;
-            g.dw_w = lw.dw15; g.dw_b = lw.dw15_b; g.dw_kw = 15; g.dw_act = ACT_SILU;
+            g.dw_w = lw.dw15; g.dw_b = lw.dw15_b; g.dw_kw = 15; g.dw_act = ACT_SILU; g.frames_eff = frames_eff;
             ASRB_TRY(launch_gemm_tc(g, st));
             TcGemmArgs h{};
             h.A = (const op16*)w.U; h.W = lw.w2_h; h.bias = lw.b2; h.res = (const op16*)w.Y;
@@ -336,7 +391,7 @@ int encoder_layers(asrb_encoder* e, const EncBuffers& w, int64_t B, int64_t T, v
             const bool to_out = last && !e->cfg.enc && out_dtype == ASRB_BF16;
             h.epilogue = TC_RES_ACT_DW; h.out = to_out ? out : w.X; h.out_bf16 = to_out;
             h.dw_w = lw.dw3; h.dw_b = lw.dw3_b; h.dw_kw = 3; h.dw_act = last ? ACT_GELU : ACT_GELU_GELU;
-            h.pos = last ? w.pos : nullptr;
+            h.pos = last ? w.pos : nullptr; h.frames_eff = frames_eff;
             h.out32 = (last && e->cfg.enc && tc_gemm_supported(D, D, TC_LN)) ? (float*)w.G : nullptr;
             ASRB_TRY(launch_gemm_tc(h, st));
             if (last && !e->cfg.enc && out_dtype != ASRB_BF16) {
@@ -421,22 +476,37 @@ extern "C" size_t asrb_encoder_workspace_bytes(const asrb_encoder* e, int64_t B,
     return enc_ws_bytes(e, B, T);
 }
 
-extern "C" int asrb_encoder_forward(asrb_encoder* e, const float* x, int64_t B, int32_t in_ch, int64_t T, void* out,
-                                    int out_dtype, void* ws, size_t ws_bytes, void* stream) {
+static int encoder_forward_impl(const char* who, asrb_encoder* e, const float* x, int64_t B, int32_t in_ch, int64_t T,
+                                const int32_t* frames, bool ragged, void* out, int out_dtype, void* ws, size_t ws_bytes, void* stream) {
     ASRB_TRY(check_forward_args(e, B, in_ch, T, out, out_dtype));
     if (B == 0 || T == 0) return ASRB_OK;
-    if (!x) return fail(ASRB_E_ARG, "asrb_encoder_forward: NULL input");
+    if (!x) return fail(ASRB_E_ARG, "%s: NULL input", who);
+    if (ragged && !frames) return fail(ASRB_E_ARG, "%s: NULL frame counts", who);
     if (!ws || ws_bytes < enc_ws_bytes(e, B, T) || ((uintptr_t)ws & 255))
-        return fail(ASRB_E_WORKSPACE, "asrb_encoder_forward: workspace NULL, not 256-B aligned or smaller than %zu B", enc_ws_bytes(e, B, T));
+        return fail(ASRB_E_WORKSPACE, "%s: workspace NULL, not 256-B aligned or smaller than %zu B", who, enc_ws_bytes(e, B, T));
     ASRB_TRY(require_sm100());
     cudaStream_t st = (cudaStream_t)stream;
     EncBuffers w = carve(e, B, T, ws, ws_bytes);
-    if (!w.ok) return fail(ASRB_E_WORKSPACE, "asrb_encoder_forward: workspace carve failed");
+    if (!w.ok) return fail(ASRB_E_WORKSPACE, "%s: workspace carve failed", who);
     const bool bf = e->cfg.compute == ASRB_BF16;
     if (in_ch != 1)
         ASRB_TRY(launch_to_channels_last(x, w.a0, bf ? DT_OP16 : DT_F32, B, in_ch, bf ? e->CP : in_ch, T,
                                          nullptr, nullptr, 0, 1, false, st));
-    return encoder_body(e, w, x, in_ch, B, T, out, out_dtype, st);
+    const int32_t* eff = nullptr;
+    if (ragged) ASRB_TRY(ragged_prepare(e, w, frames, false, 0, 1, B, T, st, &eff));
+    ASRB_TRY(encoder_body(e, w, x, in_ch, B, T, out, out_dtype, st, eff));
+    return ragged ? ragged_finish(e, w, out, out_dtype, B, T, st) : ASRB_OK;
+}
+
+extern "C" int asrb_encoder_forward(asrb_encoder* e, const float* x, int64_t B, int32_t in_ch, int64_t T, void* out,
+                                    int out_dtype, void* ws, size_t ws_bytes, void* stream) {
+    return encoder_forward_impl("asrb_encoder_forward", e, x, B, in_ch, T, nullptr, false, out, out_dtype, ws, ws_bytes, stream);
+}
+
+extern "C" int asrb_encoder_forward_ragged(asrb_encoder* e, const float* x, int64_t B, int32_t in_ch, int64_t T,
+                                           const int32_t* frames, void* out, int out_dtype, void* ws, size_t ws_bytes,
+                                           void* stream) {
+    return encoder_forward_impl("asrb_encoder_forward_ragged", e, x, B, in_ch, T, frames, true, out, out_dtype, ws, ws_bytes, stream);
 }
 
 extern "C" int asrb_encoder_forward_streams(asrb_encoder* e, int32_t n_streams, const float* const* x, const int32_t* in_ch,
@@ -474,19 +544,20 @@ extern "C" size_t asrb_pcm_to_hidden_workspace_bytes(const asrb_logmel_plan* pl,
            align_up(sizeof(uint32_t) * logmel_keys_words(pl, B, n_samples), 256) + 256;
 }
 
-extern "C" int asrb_pcm_to_hidden(const asrb_logmel_plan* pl, asrb_encoder* e, const float* pcm, int64_t B,
-                                  int64_t n_samples, int64_t pcm_stride, const int32_t* lengths, float* logmel_out,
-                                  void* out, int out_dtype, void* ws, size_t ws_bytes, void* stream) {
-    if (!pl) return fail(ASRB_E_ARG, "asrb_pcm_to_hidden: NULL plan");
-    if (n_samples < 0 || pcm_stride < n_samples) return fail(ASRB_E_ARG, "asrb_pcm_to_hidden: bad n_samples / stride");
+static int pcm_to_hidden_impl(const char* who, const asrb_logmel_plan* pl, asrb_encoder* e, const float* pcm, int64_t B,
+                              int64_t n_samples, int64_t pcm_stride, const int32_t* lengths, bool ragged, float* logmel_out,
+                              void* out, int out_dtype, void* ws, size_t ws_bytes, void* stream) {
+    if (!pl) return fail(ASRB_E_ARG, "%s: NULL plan", who);
+    if (n_samples < 0 || pcm_stride < n_samples) return fail(ASRB_E_ARG, "%s: bad n_samples / stride", who);
     const int64_t T = 1 + n_samples / pl->hop;
     ASRB_TRY(check_forward_args(e, B, pl->n_mels, T, out, out_dtype));
-    if (pl->n_mels != e->cfg.mels) return fail(ASRB_E_ARG, "asrb_pcm_to_hidden: plan has %d mels, encoder %d", pl->n_mels, e->cfg.mels);
+    if (pl->n_mels != e->cfg.mels) return fail(ASRB_E_ARG, "%s: plan has %d mels, encoder %d", who, pl->n_mels, e->cfg.mels);
     if (B == 0) return ASRB_OK;
-    if (!pcm && n_samples > 0) return fail(ASRB_E_ARG, "asrb_pcm_to_hidden: NULL pcm");
+    if (!pcm && n_samples > 0) return fail(ASRB_E_ARG, "%s: NULL pcm", who);
+    if (ragged && !lengths) return fail(ASRB_E_ARG, "%s: NULL lengths", who);
     const size_t need = asrb_pcm_to_hidden_workspace_bytes(pl, e, B, n_samples);
     if (!ws || ws_bytes < need || ((uintptr_t)ws & 255))
-        return fail(ASRB_E_WORKSPACE, "asrb_pcm_to_hidden: workspace NULL, not 256-B aligned or smaller than %zu B", need);
+        return fail(ASRB_E_WORKSPACE, "%s: workspace NULL, not 256-B aligned or smaller than %zu B", who, need);
     ASRB_TRY(require_sm100());
     cudaStream_t st = (cudaStream_t)stream;
     const size_t enc_bytes = enc_ws_bytes(e, B, T);
@@ -494,17 +565,34 @@ extern "C" int asrb_pcm_to_hidden(const asrb_logmel_plan* pl, asrb_encoder* e, c
     Arena tail((char*)ws + enc_bytes, ws_bytes - enc_bytes);
     float* mel = logmel_out ? logmel_out : tail.take<float>((size_t)B * pl->n_mels * T);
     uint32_t* keys = tail.take<uint32_t>(logmel_keys_words(pl, B, n_samples));
-    if (!w.ok || !tail.ok()) return fail(ASRB_E_WORKSPACE, "asrb_pcm_to_hidden: workspace carve failed");
+    if (!w.ok || !tail.ok()) return fail(ASRB_E_WORKSPACE, "%s: workspace carve failed", who);
+    const int32_t* eff = nullptr;
+    if (ragged) ASRB_TRY(ragged_prepare(e, w, lengths, true, n_samples, pl->hop, B, T, st, &eff));
     const bool bf = e->cfg.compute == ASRB_BF16;
     if (bf && !logmel_out) {
-        // the front end writes the stem GEMM's operand itself (bf16 channels-last) and the floor runs in place
+        // the front end writes the stem GEMM's operand itself (16-bit channels-last) and the floor runs in place
         ASRB_TRY(logmel_pass1(pl, pcm, B, n_samples, pcm_stride, lengths, nullptr, keys, st, (op16*)w.a0, e->CP));
         ASRB_TRY(logmel_floor_cl(pl, (op16*)w.a0, e->CP, keys, lengths, B, n_samples, st));
-        return encoder_body(e, w, nullptr, pl->n_mels, B, T, out, out_dtype, st);
+    } else {
+        ASRB_TRY(logmel_pass1(pl, pcm, B, n_samples, pcm_stride, lengths, mel, keys, st));
+        // the dynamic-range floor (essentials.py:489) is applied while changing layout for conv1
+        ASRB_TRY(launch_to_channels_last(mel, w.a0, bf ? DT_OP16 : DT_F32, B, pl->n_mels, bf ? e->CP : pl->n_mels, T,
+                                         keys, lengths, n_samples, pl->hop, logmel_out != nullptr, st));
     }
-    ASRB_TRY(logmel_pass1(pl, pcm, B, n_samples, pcm_stride, lengths, mel, keys, st));
-    // the dynamic-range floor (essentials.py:489) is applied while changing layout for conv1
-    ASRB_TRY(launch_to_channels_last(mel, w.a0, bf ? DT_OP16 : DT_F32, B, pl->n_mels, bf ? e->CP : pl->n_mels, T,
-                                     keys, lengths, n_samples, pl->hop, logmel_out != nullptr, st));
-    return encoder_body(e, w, nullptr, pl->n_mels, B, T, out, out_dtype, st);
+    ASRB_TRY(encoder_body(e, w, nullptr, pl->n_mels, B, T, out, out_dtype, st, eff));
+    return ragged ? ragged_finish(e, w, out, out_dtype, B, T, st) : ASRB_OK;
+}
+
+extern "C" int asrb_pcm_to_hidden(const asrb_logmel_plan* pl, asrb_encoder* e, const float* pcm, int64_t B,
+                                  int64_t n_samples, int64_t pcm_stride, const int32_t* lengths, float* logmel_out,
+                                  void* out, int out_dtype, void* ws, size_t ws_bytes, void* stream) {
+    return pcm_to_hidden_impl("asrb_pcm_to_hidden", pl, e, pcm, B, n_samples, pcm_stride, lengths, false, logmel_out, out, out_dtype,
+                              ws, ws_bytes, stream);
+}
+
+extern "C" int asrb_pcm_to_hidden_ragged(const asrb_logmel_plan* pl, asrb_encoder* e, const float* pcm, int64_t B,
+                                         int64_t n_samples, int64_t pcm_stride, const int32_t* lengths, float* logmel_out,
+                                         void* out, int out_dtype, void* ws, size_t ws_bytes, void* stream) {
+    return pcm_to_hidden_impl("asrb_pcm_to_hidden_ragged", pl, e, pcm, B, n_samples, pcm_stride, lengths, true, logmel_out, out,
+                              out_dtype, ws, ws_bytes, stream);
 }

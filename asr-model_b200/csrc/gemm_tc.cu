@@ -82,6 +82,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const int m = is_ln ? u : u / p.n_chunks;
             const int nb0 = is_ln ? (int)crank : u % p.n_chunks;
             const int b = m / p.tiles_per_utt, t0 = (m % p.tiles_per_utt) * p.rows_out - p.halo;
+            if (tile_is_padding(p.frames_eff, b, t0)) continue;               // ragged batch: nothing of this tile is needed
             for (int j = 0; j < nbu; ++j) {
                 const int n0 = (nb0 + j) * BN;
                 for (int kb = 0; kb < num_kb; ++kb) {
@@ -107,9 +108,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const bool leader = elect_one();
         constexpr uint32_t idesc = make_idesc(BN);
         int s = 0; uint32_t ph = 0; int it = 0;
-        for (int u = u_first; u < units; u += u_step, ++it) {
+        for (int u = u_first; u < units; u += u_step) {
+            if (p.frames_eff) {
+                const int m = is_ln ? u : u / p.n_chunks;
+                if (tile_is_padding(p.frames_eff, m / p.tiles_per_utt, (m % p.tiles_per_utt) * p.rows_out - p.halo)) continue;
+            }
             const int a = it % acc_stages;
             const uint32_t aph = (uint32_t)(it / acc_stages) & 1u;
+            ++it;
             mbar_wait_sleep(tempty_bar(a), aph ^ 1, 32);
             tc_fence_after();
             for (int j = 0; j < nbu; ++j) {
@@ -145,11 +151,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         unsigned char* stg = scratch + group * GROUP_SCRATCH;
         const uint32_t stg_u32 = smem_u32(stg);
         const int bar_id = 1 + group;
-        int it = 0;
-        for (int u = u_first; u < units; u += u_step, ++it) {
+        int it_next = 0;
+        for (int u = u_first; u < units; u += u_step) {
             const int m = is_ln ? u : u / p.n_chunks;
             const int nb0 = is_ln ? (int)crank : u % p.n_chunks;
             const int b = m / p.tiles_per_utt, t0 = (m % p.tiles_per_utt) * p.rows_out - p.halo;   // frame of tile row 0
+            if (tile_is_padding(p.frames_eff, b, t0)) continue;
+            const int it = it_next++;
             const int a = it % acc_stages;
             const uint32_t aph = (uint32_t)(it / acc_stages) & 1u;
             const bool row_ok = t0 + r >= 0 && t0 + r < p.T;
@@ -352,6 +360,7 @@ int tc_prepare(const TcGemmArgs& a, CUtensorMap* ma, CUtensorMap* mw, CUtensorMa
     p.tiles_per_utt = (int)((a.T + rows_out - 1) / rows_out);
     p.m_tiles = (int)(a.B * p.tiles_per_utt);
     p.n_chunks = a.N / bn; p.n_out = n_out; p.eps = a.eps; p.out_f32 = a.out_f32; p.out_bf16 = a.out_bf16;
+    p.frames_eff = a.frames_eff;
     p.cluster = (a.epilogue == TC_LN && bn == 256 && a.N == 512) ? 2 : 1;     // the 128 x 512 row block fills TMEM: split it over a CTA pair
     *bn_out = bn;
     return ASRB_OK;

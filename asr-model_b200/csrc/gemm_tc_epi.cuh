@@ -60,7 +60,14 @@ struct TcParams {
     int cluster;                 // TC_LN with N = 512: 2 CTAs own one 256-column half each and swap row sums over DSMEM
     float eps;
     int halo, rows_out;          // rows_out = 128 frames per tile, halo = 0 (kept for the tile arithmetic)
+    const int32_t* frames_eff;   // ragged batches: [B] frames per utterance that anything downstream still needs, or NULL
 };
+
+// Ragged batches: a tile whose first produced frame lies at or past the utterance's effective extent
+// is skipped by every warp role alike (the predicate only depends on the unit), so no pipeline state moves for it.
+__device__ __forceinline__ bool tile_is_padding(const int32_t* frames_eff, int b, int first_frame) {
+    return frames_eff != nullptr && first_frame >= __ldg(frames_eff + b);
+}
 
 // 32 fp32 values of one row -> 32 16-bit values into the swizzled staging tile (row r, columns cb..cb+31 of 64);
 // as_bf16 (warp-uniform): this tile is the encoder's result, otherwise the next MMA's operand

@@ -47,6 +47,7 @@ template <> struct TctCfg<TC_GLU_DW> {
 struct TctParams {
     const float* bias; const float* dw_w; const float* dw_b; const float* pos; float* out32; uint16_t* out;
     int T, K, n_out, tiles_per_utt, m_tiles, n_ct;
+    const int32_t* frames_eff;   // ragged batches: tiles whose first produced frame is past frames_eff[b] are skipped
 };
 
 // erf-GELU of x given h = x / 2 (common.cuh gelu_fast with the halving folded into the producer of h):
@@ -237,6 +238,7 @@ gemm_tct_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
         for (int u = blockIdx.x; u < units; u += gridDim.x) {
             const int m = u / p.n_ct, ct = u - m * p.n_ct;
             const int b = m / p.tiles_per_utt, tb = (m - b * p.tiles_per_utt) * C::ROWS_OUT - C::HALO;
+            if (tile_is_padding(p.frames_eff, b, tb + C::HALO)) continue;
             for (int kb = 0; kb < num_kb; ++kb) {
                 mbar_wait_sleep(empty_bar(s), ph ^ 1, 64);
                 if (leader) {
@@ -262,9 +264,14 @@ gemm_tct_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
         const bool leader = elect_one();
         constexpr uint32_t idesc = make_idesc(NF);
         int s = 0; uint32_t ph = 0; int it = 0;
-        for (int u = blockIdx.x; u < units; u += gridDim.x, ++it) {
+        for (int u = blockIdx.x; u < units; u += gridDim.x) {
+            if (p.frames_eff) {
+                const int m = u / p.n_ct, b = m / p.tiles_per_utt;
+                if (tile_is_padding(p.frames_eff, b, (m - b * p.tiles_per_utt) * C::ROWS_OUT)) continue;
+            }
             const int a = it & 1;
             const uint32_t aph = (uint32_t)(it >> 1) & 1u;
+            ++it;
             mbar_wait_sleep(tempty_bar(a), aph ^ 1, 64);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)(a * 256);
@@ -305,10 +312,12 @@ gemm_tct_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
         int ct_cur = -1;
         float hb0 = 0.f, hb1 = 0.f;                        // RES: bias / 2, -            GLU: value bias / 2, gate bias / 2
         float k[RES ? 4 : 16];                             // RES: 3 taps + bias (halved); GLU: 15 taps + bias (halved)
-        int it = 0;
-        for (int u = blockIdx.x; u < units; u += gridDim.x, ++it) {
+        int it_next = 0;
+        for (int u = blockIdx.x; u < units; u += gridDim.x) {
             const int m = u / p.n_ct, ct = u - m * p.n_ct;
             const int b = m / p.tiles_per_utt, ft = m - b * p.tiles_per_utt;
+            if (tile_is_padding(p.frames_eff, b, ft * C::ROWS_OUT)) continue;
+            const int it = it_next++;
             const int tb = ft * C::ROWS_OUT - C::HALO;      // frame of accumulator column 0
             const int a = it & 1;
             const uint32_t aph = (uint32_t)(it >> 1) & 1u;
@@ -502,7 +511,7 @@ static int launch_tct(const TcGemmArgs& a, cudaStream_t st) {
     } else { mi = mw; mr = mx; }
     TctParams p{};
     p.bias = a.bias; p.dw_w = a.dw_w; p.dw_b = a.dw_b; p.pos = a.pos; p.out32 = a.out32; p.out = (uint16_t*)a.out;
-    p.T = (int)a.T; p.K = a.K; p.n_out = n_out;
+    p.T = (int)a.T; p.K = a.K; p.n_out = n_out; p.frames_eff = a.frames_eff;
     p.tiles_per_utt = (int)((a.T + C::ROWS_OUT - 1) / C::ROWS_OUT);
     p.m_tiles = (int)(a.B * p.tiles_per_utt);
     p.n_ct = n_out / 128;

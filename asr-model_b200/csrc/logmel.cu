@@ -158,6 +158,7 @@ logmel_kernel(const LogmelParams p, int tiles_per_utt, int total_tiles) {
         int b, t0, lo, hi; int64_t s0;
         tile_geom(tile, b, t0, s0, lo, hi);
         const float* src = p.pcm + (int64_t)b * p.stride + s0;                     // span index 0 (never dereferenced outside [lo, hi))
+        if (t0 >= 1 + (int)(clamp_len(p.lengths, b, p.n_samples) / hop)) { cp_async_commit(); return false; }   // a padding tile reads no PCM
         if (vec_ok && lo == 0 && hi == span4) {
             if (tid == 0) {
                 mbar_expect_tx(pcm_bar, (uint32_t)span4 * 4u);
@@ -212,6 +213,24 @@ logmel_kernel(const LogmelParams p, int tiles_per_utt, int total_tiles) {
         const int b = tile / tiles_per_utt, t0 = (tile - b * tiles_per_utt) * FB;
         const int64_t len = clamp_len(p.lengths, b, p.n_samples);
         const int Tb = 1 + (int)(len / hop);                 // valid frames of this utterance (<= T: len <= n_samples)
+
+        if (t0 >= Tb) {
+            // ---- a tile wholly past the utterance (ragged batch): DataCollator's 0.0 padding, no transform ----
+            __syncthreads();
+            { const int next = tile + gridDim.x; if (next < total_tiles) by_tma = prefetch(next); }
+            const int nf = min(FB, p.T - t0);
+            if (p.out_cl) {
+                uint32_t* dst = reinterpret_cast<uint32_t*>(p.out_cl + ((int64_t)b * p.T + t0) * p.CP);
+                for (int i = tid; i < nf * (p.CP >> 1); i += C::THREADS) dst[i] = 0u;
+            } else {
+                for (int i = tid; i < p.M * nf; i += C::THREADS) {
+                    const int m = i / nf, f = i - m * nf;
+                    p.out[((int64_t)b * p.M + m) * p.T + t0 + f] = 0.f;
+                }
+            }
+            if (tid == 0) p.tile_min[tile] = f2key(INFINITY);
+            continue;
+        }
 
         // ---- optional: the average-pooled `waveform` feature of the bins this tile's frames name.  Bin i covers
         // samples [floor(i n / target), ceil((i + 1) n / target)): inside the staged span whenever n is a multiple

@@ -190,10 +190,36 @@ class AudioEncoder(nn.Module):
             return self._process_streams({k: v for k, v in x.items() if v is not None})
         return self._process_feature(x)
 
+    def forward_ragged(self, x: torch.Tensor, frames: torch.Tensor) -> torch.Tensor:
+        """``[B, mels, T]`` features of a padded batch + ``frames [B]`` (frames that hold audio) -> ``[B, T, dims]`` whose rows
+        ``t < frames[b]`` equal ``forward(x)`` bit for bit and whose padding rows are 0; on the tensor-core path without
+        the TransformerEncoderLayer the frame tiles of the padding are never computed."""
+        if self.training:
+            raise _lib.AsrbError("AudioEncoder implements inference semantics: call .eval() first")
+        if not x.is_cuda:
+            raise _lib.AsrbError("AudioEncoder needs a CUDA tensor: there is no CPU path")
+        x = x.float().contiguous()
+        B, Cin, T = x.shape
+        frames = torch.as_tensor(frames)
+        if frames.numel() != B:
+            raise ValueError(f"frames has {frames.numel()} entries for a batch of {B}")
+        frames = frames.to(x.device, torch.int32).contiguous()
+        h = self._handle(x.device)
+        out = torch.empty(B, T, self.dims, device=x.device, dtype=self.out_dtype)
+        ws = self._workspace(x.device, self._lib.asrb_encoder_workspace_bytes(h, B, T))
+        with torch.cuda.device(x.device):
+            _lib.check(self._lib.asrb_encoder_forward_ragged(
+                h, x.data_ptr(), B, Cin, T, frames.data_ptr(), out.data_ptr(),
+                _lib.BF16 if self.out_dtype == torch.bfloat16 else _lib.F32,
+                ws.data_ptr(), ws.numel(), _lib.stream_ptr()), "asrb_encoder_forward_ragged")
+        return out
+
     def forward_pcm(self, wave: torch.Tensor, frontend, lengths: Optional[torch.Tensor] = None,
-                    return_logmel: bool = False, out: Optional[torch.Tensor] = None):
+                    return_logmel: bool = False, out: Optional[torch.Tensor] = None, skip_padding: bool = False):
         """Fused hot path: PCM ``[B, N]`` -> hidden states ``[B, T, dims]`` in one library call
-        (``asrb_pcm_to_hidden``).  ``frontend`` is a ``LogMel`` plan with ``n_mels == mels``."""
+        (``asrb_pcm_to_hidden``).  ``frontend`` is a ``LogMel`` plan with ``n_mels == mels``.
+        ``skip_padding=True`` (needs ``lengths``): ``asrb_pcm_to_hidden_ragged`` -- the rows of each utterance's valid frames
+        are unchanged, the rows of its padding are 0, and padded frame tiles are skipped from the FFT to the last block."""
         if self.training:
             raise _lib.AsrbError("AudioEncoder implements inference semantics: call .eval() first")
         if not wave.is_cuda:
@@ -215,8 +241,11 @@ class AudioEncoder(nn.Module):
         lengths = check_lengths(lengths, B, N, wave.device)
         need = self._lib.asrb_pcm_to_hidden_workspace_bytes(frontend.handle, h, B, N)
         ws = self._workspace(wave.device, need)
+        if skip_padding and lengths is None:
+            raise ValueError("skip_padding=True needs lengths")
+        fn = self._lib.asrb_pcm_to_hidden_ragged if skip_padding else self._lib.asrb_pcm_to_hidden
         with torch.cuda.device(wave.device):
-            _lib.check(self._lib.asrb_pcm_to_hidden(
+            _lib.check(fn(
                 frontend.handle, h, wave.data_ptr(), B, N, wave.stride(0) if B > 1 else max(N, 1),
                 lengths.data_ptr() if lengths is not None else None,
                 mel.data_ptr() if mel is not None else None, out.data_ptr(),

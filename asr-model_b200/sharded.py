@@ -86,9 +86,15 @@ class PeerExchange:
     tensor-core kernels of the next step, which is what an NCCL send/recv kernel cannot do when every SM
     is occupied (measured at 8 x B200: 6.3 ms per step with NCCL point-to-point against 3.0 ms of compute).
     A device-side barrier on the signal pads closes each step's exchange.  ``slots`` gathered tensors are
-    cycled so that a peer running one step ahead never writes into a tensor the consumer may still read."""
+    cycled so that a peer running one step ahead never writes into a tensor the consumer may still read.
 
-    def __init__(self, total: int, T: int, D: int, dtype, device, group=None, slots: int = 3):
+    When the symmetric allocation has a MULTICAST mapping (NVSwitch / NVLS), a push is ONE copy-engine write through
+    the multicast address: the switch replicates it to every GPU, so a rank reads its block from HBM once and sends it
+    over its links once instead of world-1 times (at 8 GPUs: 197 MB instead of 1.38 GB of egress and of source reads
+    per step).  The write also lands on the sender's own replica, with the bytes that are already there.
+    ``multicast=False`` (or no multicast support) keeps the staggered unicast pushes."""
+
+    def __init__(self, total: int, T: int, D: int, dtype, device, group=None, slots: int = 3, multicast: bool = True):
         import torch.distributed._symmetric_memory as symm_mem
         self.group = group if group is not None else dist.group.WORLD
         self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
@@ -102,6 +108,18 @@ class PeerExchange:
             self.peers.append([h.get_buffer(r, self.shape, dtype) if r != self.rank else t for r in range(self.world)])
         self.stream = torch.cuda.Stream(device)
         self.step = 0
+        self.mc_ptrs = [int(getattr(h, "multicast_ptr", 0) or 0) for h in self.hdls] if multicast and self.world > 2 else []
+        self._memcpy = None
+        if self.mc_ptrs and all(self.mc_ptrs):
+            import ctypes
+            try:
+                rt = ctypes.CDLL("libcudart.so.12")
+                rt.cudaMemcpyAsync.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p]
+                rt.cudaMemcpyAsync.restype = ctypes.c_int
+                self._memcpy = rt.cudaMemcpyAsync
+            except OSError:
+                self._memcpy = None
+        self.row_bytes = T * D * torch.empty(0, dtype=dtype).element_size()
 
     def next_slot(self) -> int:
         k = self.step % len(self.bufs)
@@ -115,6 +133,12 @@ class PeerExchange:
         with torch.cuda.stream(self.stream):
             self.stream.wait_event(ev)
             src = self.bufs[slot][lo:hi]
+            if self._memcpy is not None:                        # one write, replicated by the switch
+                rc = self._memcpy(self.mc_ptrs[slot] + lo * self.row_bytes, src.data_ptr(), (hi - lo) * self.row_bytes, 3,
+                                  self.stream.cuda_stream)
+                if rc != 0:
+                    raise RuntimeError(f"cudaMemcpyAsync to the multicast mapping failed ({rc})")
+                return
             for k in range(1, self.world):                      # staggered so the peers' ingress ports are used evenly
                 r = (self.rank + k) % self.world
                 self.peers[slot][r][lo:hi].copy_(src, non_blocking=True)
@@ -149,7 +173,7 @@ class ShardedEncoder:
 
     def __init__(self, compute: Callable[..., torch.Tensor], group=None, micro: int = 0, gather: bool = True,
                  shape_of: Optional[Callable[[torch.Tensor], Tuple[int, int, torch.dtype]]] = None,
-                 overlap_steps: bool = False, exchange: str = "auto", slots: int = 3):
+                 overlap_steps: bool = False, exchange: str = "auto", slots: int = 3, multicast: bool = True):
         """``overlap_steps``: do not wait for a call's exchange before returning; it is waited for at the
         end of the NEXT call (or by ``finish()``), so the gather of step i rides under the compute of
         step i+1.  The local block of the returned tensor is always valid on the current stream; the
@@ -160,7 +184,7 @@ class ShardedEncoder:
         # "peer": copy-engine pushes through symmetric memory (PeerExchange); "nccl": grouped send/recv;
         # "auto": peer on the NCCL backend when shape_of is known and the rendezvous succeeds, else nccl
         self.exchange = exchange
-        self.slots = slots
+        self.slots, self.multicast = slots, multicast
         self._peer: Optional[PeerExchange] = None
         self._peer_key = None
 
@@ -172,7 +196,7 @@ class ShardedEncoder:
             self.finish()
             peer, err = None, None
             try:
-                peer = PeerExchange(total, T, D, dt, device, self.group, slots=self.slots)
+                peer = PeerExchange(total, T, D, dt, device, self.group, slots=self.slots, multicast=self.multicast)
             except Exception as e:                   # no symmetric memory on this system
                 err = e
             # every rank must end up on the same protocol: agree on the outcome before anyone uses it

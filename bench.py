@@ -19,7 +19,8 @@ weights.  A step = one pass of the hot path (PCM -> hidden states) over one batc
   cpu_baseline / --impl reference   the UNMODIFIED reference modules (baseline/ref_harness.py) on this box's host cores;
               the oracle port only if no copy of the reference is reachable.
   extras (N = 1, on by default)     gpu_eager_baseline (the reference in PyTorch eager on this GPU: fp32/TF32 and bf16
-              autocast), enc1 (with the TransformerEncoderLayer), config4 (wide encoder), frontend_sweep (config 3).
+              autocast), enc1 (with the TransformerEncoderLayer), config4 (wide encoder), frontend_sweep (config 3),
+              ragged (padded batch with and without skipping the padding).
   strong_scaling (every N)          BASELINE config 5: 2048 x 30 s in total, sharded over the N ranks, micro-batches of 64,
               encoder outputs gathered on every rank.
 
@@ -446,6 +447,16 @@ def run_extras(torch, ab, synth, LogMel, enc, fe, pcm, args, pk, dev):
         out["enc1"] = {"what": "same workload with enc=True (TransformerEncoderLayer: tcgen05 flash attention + FFN 2048)", "ms_per_step": ms,
                        "audio_s_per_s": B * SECS / (ms * 1e-3), "tflops": fl / ms / 1e9, "frac_sustained": fl / ms / 1e9 / pk["tf_sustained"]}
         del m
+    # --- ragged batch: clips of 5 .. 30 s padded to 30 s; default path encodes the padding like the
+    #     reference, skip_padding computes only the frame tiles valid frames depend on
+    if not args.enc:
+        lengths = torch.linspace(5 * SR, N, B).long()
+        ms_pad = timed_ms(torch, lambda: enc.forward_pcm(pcm, fe, lengths=lengths.to(dev)), 10, 3)
+        ms_skip = timed_ms(torch, lambda: enc.forward_pcm(pcm, fe, lengths=lengths.to(dev), skip_padding=True), 10, 3)
+        valid_s = float(lengths.sum()) / SR
+        out["ragged"] = {"what": "64 clips of 5 .. 30 s (uniform) padded to 30 s: default (padding encoded, as the reference) vs skip_padding",
+                         "valid_audio_s": valid_s, "ms_padding_encoded": ms_pad, "ms_padding_skipped": ms_skip,
+                         "valid_audio_s_per_s_skipped": valid_s / (ms_skip * 1e-3), "valid_audio_s_per_s_padded": valid_s / (ms_pad * 1e-3)}
     # --- BASELINE config 3: front end alone, 256 x 30 s
     pcm3 = synth.white_noise_batch(256, N, device=dev)
     sweep = []

@@ -143,6 +143,16 @@ int asrb_encoder_forward(asrb_encoder* enc, const float* x, int64_t batch, int32
                          int64_t frames, void* out, int out_dtype,
                          void* workspace, size_t workspace_bytes, void* stream);
 
+/* Ragged batches (DataCollator pads every clip to the longest with 0.0, essentials.py:555-572):
+ * frames [batch] int32 device = frames of each utterance that hold audio.  Output rows t < frames[b] equal
+ * asrb_encoder_forward's bit for bit; rows t >= frames[b] are set to 0 instead of the encoding of the padding.  On the
+ * tensor-core path without the TransformerEncoderLayer every frame tile past frames[b] + 9 * layer + 1 (the widest cone a
+ * valid output frame depends on) is skipped by every kernel of the stack; with enc = 1 (attention sees every frame,
+ * model.py:163) and on the fp32 path everything is computed and only the zeroing differs. */
+int asrb_encoder_forward_ragged(asrb_encoder* enc, const float* x, int64_t batch, int32_t in_ch, int64_t frames_total,
+                                const int32_t* frames, void* out, int out_dtype,
+                                void* workspace, size_t workspace_bytes, void* stream);
+
 /* Several feature streams of the same shape through ONE pass of the layer stack (Model.forward / generate encode
  * the TensorDict {a, b, c} = spectrogram / waveform / pitch with the same encoder, model.py:165-167, 657-665): stream s
  * is x[s] [batch][in_ch[s]][frames] (in_ch = mels -> conv1, 1 -> conv2); out is [n_streams * batch][frames][dims], stream s
@@ -162,6 +172,15 @@ int asrb_pcm_to_hidden(const asrb_logmel_plan* plan, asrb_encoder* enc,
                        const int32_t* lengths, float* logmel_out /* may be NULL */,
                        void* out, int out_dtype,
                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* The same for ragged batches: lengths [batch] int32 device is required; valid rows (t < 1 + lengths[b] / hop) are bit-equal
+ * to asrb_pcm_to_hidden with the same lengths, the rows of the padding are 0, and padded frame tiles are skipped from the
+ * FFT to the last conv block (see asrb_encoder_forward_ragged). */
+int asrb_pcm_to_hidden_ragged(const asrb_logmel_plan* plan, asrb_encoder* enc,
+                              const float* pcm, int64_t batch, int64_t n_samples, int64_t pcm_stride,
+                              const int32_t* lengths, float* logmel_out /* may be NULL */,
+                              void* out, int out_dtype,
+                              void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Secondary: the `attention` block's live branch applied to encoded audio

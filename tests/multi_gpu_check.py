@@ -33,11 +33,11 @@ def main():
     shape_of = lambda w: (fe.num_frames(w.shape[1]), 256, torch.bfloat16)
     hot = lambda w, out=None: enc.forward_pcm(w, fe, out=out)
     ok = True
-    for exchange in ("peer", "nccl"):
+    for exchange, mc in (("peer", True), ("peer", False), ("nccl", False)):      # multicast push (world > 2), unicast pushes, NCCL
         for micro in (0, 2):
-            se = ShardedEncoder(hot, micro=micro, shape_of=shape_of, exchange=exchange)
+            se = ShardedEncoder(hot, micro=micro, shape_of=shape_of, exchange=exchange, multicast=mc)
             ok &= bool(torch.equal(se(waves[lo:hi], total=total), ref))
-        se = ShardedEncoder(hot, shape_of=shape_of, overlap_steps=True, exchange=exchange)
+        se = ShardedEncoder(hot, shape_of=shape_of, overlap_steps=True, exchange=exchange, multicast=mc)
         outs = [se(waves[lo:hi] * (1.0 - 0.1 * i), total=total) for i in range(4)]   # more steps than gathered slots
         se.finish()
         torch.cuda.synchronize()

@@ -241,3 +241,33 @@ def test_attention_rotary_block_matches_reference_fixture(ab, golden):
     a.load_state_dict(sd)
     x = torch.randn(2, 301, 256, generator=torch.Generator().manual_seed(2))
     assert float((a(x.cuda()).cpu() - oracle.attention_forward(sd, x, 4)).abs().max()) <= 2e-4
+
+
+@pytest.mark.parametrize("D,L,enc,compute", [(512, 4, False, "bf16"), (256, 2, False, "bf16"), (256, 2, True, "bf16"), (128, 2, False, "fp32")])
+def test_ragged_batch_skips_padding_without_touching_valid_frames(ab, D, L, enc, compute):
+    """a padded batch with per-utterance lengths.  Rows of valid frames must equal the default path bit
+    for bit (which computes the padding like the reference does), rows of the padding must be 0 -- through the fused PCM
+    entry point and through the feature entry point; poisoned workspace shows that no skipped tile leaks into a valid row."""
+    from asr_model_b200.frontend import LogMel
+    N = 160 * 1500
+    sd = oracle.random_encoder_state_dict(80, D, L, enc, seed=31, perturb=True)
+    m = _enc(ab, sd, 80, D, 4, L, enc, compute)
+    fe = LogMel(80, 400)
+    waves = synth.make_batch("WHTW2H", N).cuda()
+    lengths = torch.tensor([N, 160 * 700 + 13, 160 * 37, 0, 160 * 1279, 160 * 1499 + 159])
+    frames = 1 + lengths // 160
+    full = m.forward_pcm(waves, fe, lengths=lengths).clone()
+    if m._ws:                                            # poison the workspace: stale NaNs must stay inside skipped tiles
+        for ws in m._ws.values():
+            ws.view(torch.int16)[: ws.numel() // 2].fill_(0x7FFF if compute == "fp32" else 0x7E00)
+    rag = m.forward_pcm(waves, fe, lengths=lengths, skip_padding=True)
+    for b in range(len(lengths)):
+        v = int(frames[b])
+        assert torch.equal(rag[b, :v], full[b, :v]), b
+        assert torch.all(rag[b, v:] == 0), b
+    mel = fe(waves, lengths)
+    rag2 = m.forward_ragged(mel, frames)
+    base = m(mel)
+    for b in range(len(lengths)):
+        v = int(frames[b])
+        assert torch.equal(rag2[b, :v], base[b, :v]) and torch.all(rag2[b, v:] == 0), b
