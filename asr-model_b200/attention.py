@@ -2,7 +2,11 @@
 audio (model.py:234-317 with ``n_type="rmsnorm"``, ``xa=None, mask=None, pt=None``) including
 ``rotary`` (model.py:171-214).  Parameter names match the reference module so its
 ``state_dict`` loads unchanged.  Batched = the reference's B=1 semantics per utterance
-(its own broadcast is only defined for B == 1)."""
+(its own broadcast is only defined for B == 1).
+
+``compute="fp32"`` is the CUDA-core variant (<= 1e-4 of the reference); ``compute="bf16"`` the tensor-core variant, which
+also exposes the K|V reuse of SURVEY.md section 8f rank 3: ``kv = att.encode_kv(audio)`` once, then ``att(x, kv=kv)`` for every
+query sequence that attends the same encoded audio (the reference recomputes the K|V branch on every call)."""
 from __future__ import annotations
 
 import ctypes as C
@@ -18,11 +22,13 @@ class _Named(nn.Sequential):
 
 
 class AudioAttention(nn.Module):
-    def __init__(self, dims: int, head: int, layer: int = 1, n_type: str = "rmsnorm"):
+    def __init__(self, dims: int, head: int, layer: int = 1, n_type: str = "rmsnorm", compute: str = "fp32"):
         super().__init__()
         if n_type != "rmsnorm":
             raise NotImplementedError("only n_type='rmsnorm' is deterministic in the reference")
-        self.dims, self.head = dims, head
+        if compute not in ("fp32", "bf16"):
+            raise ValueError("compute must be 'fp32' or 'bf16'")
+        self.dims, self.head, self.compute = dims, head, compute
         hd = dims // head
         self.q = _Named(nn.RMSNorm(dims), nn.Linear(dims, dims))
         self.kv = _Named(nn.RMSNorm(dims), nn.Linear(dims, dims * 2))
@@ -45,7 +51,8 @@ class AudioAttention(nn.Module):
         sd["__rot_freqs"] = (200 * g / 1000).float()
         n, names, ptrs, nums, keep = _lib.state_dict_arrays(sd)
         h = C.c_void_p()
-        _lib.check(self._lib.asrb_attention_create(self.dims, self.head, _lib.F32, n, names, ptrs, nums, C.byref(h)),
+        _lib.check(self._lib.asrb_attention_create(self.dims, self.head, _lib.BF16 if self.compute == "bf16" else _lib.F32,
+                                                   n, names, ptrs, nums, C.byref(h)),
                    "asrb_attention_create")
         self._handle = h
         return self
@@ -66,7 +73,32 @@ class AudioAttention(nn.Module):
         self._release() if self._lib is not None else None
         return r
 
-    def forward(self, x: torch.Tensor) -> torch.Tensor:
+    def _workspace(self, device, B, T):
+        need = self._lib.asrb_attention_workspace_bytes(self._handle, B, T)
+        if self._ws is None or self._ws.numel() < need or self._ws.device != device:
+            self._ws = torch.empty(max(need, 256), dtype=torch.uint8, device=device)
+        return self._ws
+
+    def encode_kv(self, xa: torch.Tensor) -> torch.Tensor:
+        """K (rotary + per-head norm applied) | V of ``xa [B, Tk, D]`` as an opaque 16-bit ``[B, Tk, 2 D]`` cache tensor."""
+        if self.compute != "bf16":
+            raise _lib.AsrbError("the K|V cache belongs to the tensor-core variant (compute='bf16')")
+        if not xa.is_cuda:
+            raise _lib.AsrbError("AudioAttention needs a CUDA tensor: there is no CPU path")
+        xa = xa.float().contiguous()
+        B, Tk, D = xa.shape
+        with torch.cuda.device(xa.device):
+            if self._handle is None:
+                self.prepare()
+            kv = torch.empty(B, Tk, 2 * D, dtype=_lib.operand_dtype(), device=xa.device)
+            ws = self._workspace(xa.device, B, Tk)
+            _lib.check(self._lib.asrb_attention_encode_kv(self._handle, xa.data_ptr(), B, Tk, kv.data_ptr(), ws.data_ptr(),
+                                                          ws.numel(), _lib.stream_ptr()), "asrb_attention_encode_kv")
+        return kv
+
+    def forward(self, x: torch.Tensor, kv: torch.Tensor = None) -> torch.Tensor:
+        """``x [B, T, D]`` -> ``[B, T, D]`` fp32.  ``kv``: a cache from ``encode_kv`` -- the queries of ``x`` then attend the
+        cached sequence instead of ``x`` itself (model.py:258-262 with ``xa`` given)."""
         if not x.is_cuda:
             raise _lib.AsrbError("AudioAttention needs a CUDA tensor: there is no CPU path")
         x = x.float().contiguous()
@@ -75,10 +107,15 @@ class AudioAttention(nn.Module):
             if self._handle is None:
                 self.prepare()
             out = torch.empty_like(x)
-            need = self._lib.asrb_attention_workspace_bytes(self._handle, B, T)
-            if self._ws is None or self._ws.numel() < need or self._ws.device != x.device:
-                self._ws = torch.empty(max(need, 256), dtype=torch.uint8, device=x.device)
-            _lib.check(self._lib.asrb_attention_forward(self._handle, x.data_ptr(), B, T, out.data_ptr(),
-                                                        self._ws.data_ptr(), self._ws.numel(), _lib.stream_ptr()),
-                       "asrb_attention_forward")
+            ws = self._workspace(x.device, B, T)
+            if kv is None:
+                _lib.check(self._lib.asrb_attention_forward(self._handle, x.data_ptr(), B, T, out.data_ptr(),
+                                                            ws.data_ptr(), ws.numel(), _lib.stream_ptr()),
+                           "asrb_attention_forward")
+            else:
+                if kv.shape[0] != B or kv.shape[2] != 2 * D or not kv.is_contiguous():
+                    raise ValueError("kv must be the [B, Tk, 2 D] tensor encode_kv returned for the same batch")
+                _lib.check(self._lib.asrb_attention_forward_cached(self._handle, x.data_ptr(), B, T, kv.data_ptr(), kv.shape[1],
+                                                                   out.data_ptr(), ws.data_ptr(), ws.numel(), _lib.stream_ptr()),
+                           "asrb_attention_forward_cached")
         return out

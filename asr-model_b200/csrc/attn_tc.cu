@@ -24,7 +24,9 @@ template <int HD> struct AttnCfg {
     static_assert(SMEM <= 227 * 1024, "shared memory budget");
 };
 
-struct AttnParams { int T, D, H, n_kv; float scale_log2; op16* out; };
+// Tq query frames against Tk key/value frames; q / k / v of head h start at columns q_col0 / k_col0 / v_col0 + h * HD of their
+// tensors (packed qkv [B][T][3D]: 0 / D / 2D of one tensor; a cached K|V [B][Tk][2D] next to separate queries: 0 / 0 / D)
+struct AttnParams { int Tq, Tk, D, H, n_kv, q_col0, k_col0, v_col0; float scale_log2; op16* out; };
 
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) {
     const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
@@ -57,7 +59,7 @@ __device__ __forceinline__ float ex2f(float x) {
 
 template <int HD>
 __global__ void __launch_bounds__(AttnCfg<HD>::THREADS, 1)
-attn_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParams p) {
+attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv, const AttnParams p) {
     using C = AttnCfg<HD>;
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* s_q = smem;                                   // [SUB][128][128 B]
@@ -81,7 +83,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParams p) 
     const int q0 = blockIdx.x * BM, h = blockIdx.y, b = blockIdx.z;
     const int n_kv = p.n_kv;
 
-    if (warp == 0 && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_qkv) : "memory");
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_q) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_kv) : "memory");
+    }
     if (warp == 1 && lane == 0) {
         mbar_init(q_full, 1);
         for (int s = 0; s < 2; ++s) {
@@ -106,17 +111,17 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParams p) 
         if (lane == 0) {
             mbar_expect_tx(q_full, C::Q_BYTES);
             for (int s = 0; s < C::SUB; ++s)
-                tma_load_3d(smem_u32(s_q + s * (BM * 128)), &map_qkv, h * HD + s * 64, q0, b, q_full);
+                tma_load_3d(smem_u32(s_q + s * (BM * 128)), &map_q, p.q_col0 + h * HD + s * 64, q0, b, q_full);
             for (int j = 0; j < n_kv; ++j) {
                 const int st = j & 1; const uint32_t ph = (uint32_t)(j >> 1) & 1u;
                 mbar_wait(k_empty(st), ph ^ 1);
                 mbar_expect_tx(k_full(st), C::KV_BYTES);
                 for (int s = 0; s < C::SUB; ++s)
-                    tma_load_3d(smem_u32(s_k + st * C::KV_BYTES + s * (BM * 128)), &map_qkv, p.D + h * HD + s * 64, j * BM, b, k_full(st));
+                    tma_load_3d(smem_u32(s_k + st * C::KV_BYTES + s * (BM * 128)), &map_kv, p.k_col0 + h * HD + s * 64, j * BM, b, k_full(st));
                 mbar_wait(v_empty(st), ph ^ 1);
                 mbar_expect_tx(v_full(st), C::KV_BYTES);
                 for (int s = 0; s < C::SUB; ++s)
-                    tma_load_3d(smem_u32(s_v + st * C::KV_BYTES + s * (BM * 128)), &map_qkv, 2 * p.D + h * HD + s * 64, j * BM, b, v_full(st));
+                    tma_load_3d(smem_u32(s_v + st * C::KV_BYTES + s * (BM * 128)), &map_kv, p.v_col0 + h * HD + s * 64, j * BM, b, v_full(st));
             }
         }
     } else if (warp == 1) {
@@ -170,7 +175,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParams p) 
             tc_fence_after();
             const uint32_t ts = tm_s + lane_off + (uint32_t)(st * BM);
             const int kbase = j * BM;
-            const bool tail = kbase + BM > p.T;                      // keys >= T are padding: mask them
+            const bool tail = kbase + BM > p.Tk;                     // keys >= Tk are padding: mask them
             // ---- pass A: row max of the scaled scores ----
             float mx = -INFINITY;
 #pragma unroll
@@ -179,7 +184,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParams p) 
                 tmem_ld32(ts + c, v);
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
-                    const float sv = (tail && kbase + c + i >= p.T) ? -INFINITY : v[i] * p.scale_log2;
+                    const float sv = (tail && kbase + c + i >= p.Tk) ? -INFINITY : v[i] * p.scale_log2;
                     mx = fmaxf(mx, sv);
                 }
             }
@@ -214,7 +219,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParams p) 
                 float rs = 0.f;
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
-                    const float sv = (tail && kbase + c + i >= p.T) ? -INFINITY : v[i] * p.scale_log2;
+                    const float sv = (tail && kbase + c + i >= p.Tk) ? -INFINITY : v[i] * p.scale_log2;
                     v[i] = ex2f(sv - m_used);
                     rs += v[i];
                 }
@@ -242,8 +247,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParams p) 
         for (int c = 0; c < HD; c += 32) {
             float o[32];
             tmem_ld32(tm_o + lane_off + c, o);
-            if (t < p.T) {
-                op16* dst = p.out + ((int64_t)b * p.T + t) * p.D + h * HD + c;
+            if (t < p.Tq) {
+                op16* dst = p.out + ((int64_t)b * p.Tq + t) * p.D + h * HD + c;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     uint4 q;
@@ -269,28 +274,38 @@ bool attention_tc_supported(int D, int H) {
 }
 
 template <int HD>
-static int launch_attn(const CUtensorMap& map, const AttnParams& p, int64_t B, cudaStream_t st) {
+static int launch_attn(const CUtensorMap& mq, const CUtensorMap& mkv, const AttnParams& p, int64_t B, cudaStream_t st) {
     auto kern = attn_tc_kernel<HD>;
     ASRB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<HD>::SMEM));
-    dim3 grid((unsigned)((p.T + BM - 1) / BM), (unsigned)p.H, (unsigned)B);
-    kern<<<grid, AttnCfg<HD>::THREADS, AttnCfg<HD>::SMEM, st>>>(map, p);
+    dim3 grid((unsigned)((p.Tq + BM - 1) / BM), (unsigned)p.H, (unsigned)B);
+    kern<<<grid, AttnCfg<HD>::THREADS, AttnCfg<HD>::SMEM, st>>>(mq, mkv, p);
     ASRB_LAUNCH_CHECK();
     return ASRB_OK;
 }
 
+// q [B][Tq][ldq] and kv [B][Tk][ldkv] op16 (head h of q / k / v at columns *_col0 + h * hd) -> out [B][Tq][D] op16,
+// softmax(q k^T * scale) v per head, no mask.
+int launch_attention_tc_ex(const void* q, int ldq, int q_col0, const void* kv, int ldkv, int k_col0, int v_col0, void* out,
+                           int64_t B, int64_t Tq, int64_t Tk, int D, int H, float scale, cudaStream_t st) {
+    if (!attention_tc_supported(D, H) || (ldq & 7) || (ldkv & 7))
+        return fail(ASRB_E_ARG, "tcgen05 attention: head_dim %d unsupported (64 or 128)", H ? D / H : 0);
+    if (B <= 0 || Tq <= 0 || Tk <= 0) return ASRB_OK;
+    if (B > 65535) return fail(ASRB_E_ARG, "tcgen05 attention: batch %lld > 65535", (long long)B);
+    CUtensorMap mq, mkv;
+    ASRB_TRY(make_act_map(&mq, q, B, Tq, ldq));
+    ASRB_TRY(make_act_map(&mkv, kv, B, Tk, ldkv));
+    AttnParams p;
+    p.Tq = (int)Tq; p.Tk = (int)Tk; p.D = D; p.H = H; p.n_kv = (int)((Tk + BM - 1) / BM);
+    p.q_col0 = q_col0; p.k_col0 = k_col0; p.v_col0 = v_col0;
+    p.scale_log2 = scale * 1.4426950408889634f; p.out = (op16*)out;
+    ProfScope ps("attention_tc", st, 4.0 * B * (double)Tq * Tk * D, 2.0 * B * D * (2.0 * Tq + 2.0 * Tk));
+    if (D / H == 128) return launch_attn<128>(mq, mkv, p, B, st);
+    return launch_attn<64>(mq, mkv, p, B, st);
+}
+
 // qkv [B][T][3D] op16 (q | k | v) -> out [B][T][D] op16, softmax(q k^T * scale) v per head.
 int launch_attention_tc(const void* qkv, void* out, int64_t B, int64_t T, int D, int H, float scale, cudaStream_t st) {
-    if (!attention_tc_supported(D, H)) return fail(ASRB_E_ARG, "tcgen05 attention: head_dim %d unsupported (64 or 128)", H ? D / H : 0);
-    if (B <= 0 || T <= 0) return ASRB_OK;
-    if (B > 65535) return fail(ASRB_E_ARG, "tcgen05 attention: batch %lld > 65535", (long long)B);
-    CUtensorMap map;
-    ASRB_TRY(make_act_map(&map, qkv, B, T, 3 * D));
-    AttnParams p;
-    p.T = (int)T; p.D = D; p.H = H; p.n_kv = (int)((T + BM - 1) / BM);
-    p.scale_log2 = scale * 1.4426950408889634f; p.out = (op16*)out;
-    ProfScope ps("attention_tc", st, 4.0 * B * (double)T * T * D, 2.0 * B * T * D * 4.0);
-    if (D / H == 128) return launch_attn<128>(map, p, B, st);
-    return launch_attn<64>(map, p, B, st);
+    return launch_attention_tc_ex(qkv, 3 * D, 0, qkv, 3 * D, D, 2 * D, out, B, T, T, D, H, scale, st);
 }
 
 }  // namespace asrb

@@ -451,7 +451,8 @@ int launch_attention_simt(const void* qkv, void* out, DType dt, int64_t B, int64
 // ------------------------------------------------------------------------------------------
 // Secondary block: RMSNorm rows; rotary (model.py:198-214) + per-head RMSNorm (model.py:307)
 // ------------------------------------------------------------------------------------------
-__global__ void rmsnorm_kernel(const float* __restrict__ x, const float* __restrict__ w, float* __restrict__ out,
+template <class TO>
+__global__ void rmsnorm_kernel(const float* __restrict__ x, const float* __restrict__ w, TO* __restrict__ out,
                                int64_t rows, int D, float eps) {
     const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) return;
@@ -459,18 +460,21 @@ __global__ void rmsnorm_kernel(const float* __restrict__ x, const float* __restr
     float s = 0.f;
     for (int c = lane; c < D; c += 32) { const float v = x[row * D + c]; s = fmaf(v, v, s); }
     const float r = rsqrtf(warp_sum(s) / (float)D + eps);
-    for (int c = lane; c < D; c += 32) out[row * D + c] = x[row * D + c] * r * w[c];
+    for (int c = lane; c < D; c += 32) io<TO>::st(out + row * D + c, x[row * D + c] * r * w[c]);
 }
 
-int launch_rmsnorm(const float* x, const float* w, float* out, int64_t rows, int D, cudaStream_t st) {
-    ProfScope ps("rmsnorm", st, 0.0, (double)rows * D * 8.0);
-    rmsnorm_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(x, w, out, rows, D, 1.1920928955078125e-07f);
+int launch_rmsnorm(const float* x, const float* w, void* out, DType o_dt, int64_t rows, int D, cudaStream_t st) {
+    ProfScope ps("rmsnorm", st, 0.0, (double)rows * D * (o_dt == DT_F32 ? 8.0 : 6.0));
+    const unsigned grid = (unsigned)((rows + 7) / 8);
+    if (o_dt == DT_F32) rmsnorm_kernel<float><<<grid, 256, 0, st>>>(x, w, (float*)out, rows, D, 1.1920928955078125e-07f);
+    else rmsnorm_kernel<op16><<<grid, 256, 0, st>>>(x, w, (op16*)out, rows, D, 1.1920928955078125e-07f);
     ASRB_LAUNCH_CHECK();
     return ASRB_OK;
 }
 
 // One warp per (row = (b,t), head).  x <- rmsnorm_hd( (x * pre_scale) (*) polar(||xa_t||, t f_j) ) * ln_w
-__global__ void rotary_headnorm_kernel(float* __restrict__ x_all, int64_t ld, const float* __restrict__ xa,
+template <class TX>
+__global__ void rotary_headnorm_kernel(TX* __restrict__ x_all, int64_t ld, const float* __restrict__ xa,
                                        const float* __restrict__ ln_w, const float* __restrict__ freqs,
                                        int64_t rows, int64_t T, int D, int H, float pre_scale, float eps) {
     const int64_t wid = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -483,29 +487,44 @@ __global__ void rotary_headnorm_kernel(float* __restrict__ x_all, int64_t ld, co
     float s = 0.f;
     for (int c = lane; c < D; c += 32) { const float v = xa[row * D + c]; s = fmaf(v, v, s); }
     const float mag = sqrtf(warp_sum(s));                       // torch.norm(xa, dim=-1) (model.py:201)
-    float* x = x_all + row * ld + h * hd;
+    TX* x = x_all + row * ld + h * hd;
+    float yv[4];                                                // hd <= 128: up to two pairs per lane, kept in fp32
     float ss = 0.f;
-    for (int j = lane; j < hd / 2; j += 32) {
-        const float ang = (float)t * freqs[j];
-        float sn, cs;
-        sincosf(ang, &sn, &cs);
-        const float fr = mag * cs, fi = mag * sn;               // torch.polar(m, f)
-        const float xr = x[2 * j] * pre_scale, xi = x[2 * j + 1] * pre_scale;
-        const float yr = xr * fr - xi * fi, yi = xr * fi + xi * fr;
-        x[2 * j] = yr; x[2 * j + 1] = yi;
-        ss = fmaf(yr, yr, fmaf(yi, yi, ss));
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int j = lane + 32 * i;
+        yv[2 * i] = yv[2 * i + 1] = 0.f;
+        if (j < hd / 2) {
+            const float ang = (float)t * freqs[j];
+            float sn, cs;
+            sincosf(ang, &sn, &cs);
+            const float fr = mag * cs, fi = mag * sn;           // torch.polar(m, f)
+            const float xr = io<TX>::ld(x + 2 * j) * pre_scale, xi = io<TX>::ld(x + 2 * j + 1) * pre_scale;
+            yv[2 * i] = xr * fr - xi * fi; yv[2 * i + 1] = xr * fi + xi * fr;
+            ss = fmaf(yv[2 * i], yv[2 * i], fmaf(yv[2 * i + 1], yv[2 * i + 1], ss));
+        }
     }
     const float r = rsqrtf(warp_sum(ss) / (float)hd + eps);
-    __syncwarp();
-    for (int c = lane; c < hd; c += 32) x[c] = x[c] * r * ln_w[c];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int j = lane + 32 * i;
+        if (j < hd / 2) {
+            io<TX>::st(x + 2 * j, yv[2 * i] * r * ln_w[2 * j]);
+            io<TX>::st(x + 2 * j + 1, yv[2 * i + 1] * r * ln_w[2 * j + 1]);
+        }
+    }
 }
 
-int launch_rotary_headnorm(float* x, int64_t ld, const float* xa, const float* ln_w, const float* freqs,
+int launch_rotary_headnorm(void* x, DType dt, int64_t ld, const float* xa, const float* ln_w, const float* freqs,
                            int64_t B, int64_t T, int D, int H, float pre_scale, cudaStream_t st) {
     const int64_t warps = B * T * H;
-    ProfScope ps("rotary_headnorm", st, 0.0, (double)B * T * D * 12.0);
-    rotary_headnorm_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(x, ld, xa, ln_w, freqs, B * T, T, D, H,
-                                                                         pre_scale, 1.1920928955078125e-07f);
+    if (D / H > 128) return fail(ASRB_E_ARG, "rotary: head_dim %d > 128", D / H);
+    ProfScope ps("rotary_headnorm", st, 0.0, (double)B * T * D * (dt == DT_F32 ? 12.0 : 8.0));
+    const unsigned grid = (unsigned)((warps + 7) / 8);
+    if (dt == DT_F32)
+        rotary_headnorm_kernel<float><<<grid, 256, 0, st>>>((float*)x, ld, xa, ln_w, freqs, B * T, T, D, H, pre_scale, 1.1920928955078125e-07f);
+    else
+        rotary_headnorm_kernel<op16><<<grid, 256, 0, st>>>((op16*)x, ld, xa, ln_w, freqs, B * T, T, D, H, pre_scale, 1.1920928955078125e-07f);
     ASRB_LAUNCH_CHECK();
     return ASRB_OK;
 }

@@ -51,11 +51,14 @@ int launch_attention_simt_ex(const void* q, const void* k, const void* v, int64_
 // Flash-style attention on tcgen05/TMEM (attn_tc.cu): op16 qkv [B][T][3D] -> op16 out [B][T][D]; head_dim 64 | 128
 bool attention_tc_supported(int D, int H);
 int launch_attention_tc(const void* qkv, void* out, int64_t B, int64_t T, int D, int H, float scale, cudaStream_t st);
+// general form: separate query and key/value tensors (cross-attention against a cached K|V), Tq != Tk allowed
+int launch_attention_tc_ex(const void* q, int ldq, int q_col0, const void* kv, int ldkv, int k_col0, int v_col0, void* out,
+                           int64_t B, int64_t Tq, int64_t Tk, int D, int H, float scale, cudaStream_t st);
 
-// RMSNorm rows (nn.RMSNorm, eps = fp32 machine eps): out = x / sqrt(mean(x^2)+eps) * w
-int launch_rmsnorm(const float* x, const float* w, float* out, int64_t rows, int D, cudaStream_t st);
-// rotary (model.py:198-214) + per-head RMSNorm (model.py:307) in place on x [B*T][ld], heads at h*hd
-int launch_rotary_headnorm(float* x, int64_t ld, const float* xa, const float* ln_w, const float* freqs,
+// RMSNorm rows (nn.RMSNorm, eps = fp32 machine eps): out = x / sqrt(mean(x^2)+eps) * w; out fp32 or op16 (an MMA operand)
+int launch_rmsnorm(const float* x, const float* w, void* out, DType o_dt, int64_t rows, int D, cudaStream_t st);
+// rotary (model.py:198-214) + per-head RMSNorm (model.py:307) in place on x [B*T][ld] (fp32 or op16), heads at h*hd
+int launch_rotary_headnorm(void* x, DType dt, int64_t ld, const float* xa, const float* ln_w, const float* freqs,
                            int64_t B, int64_t T, int D, int H, float pre_scale, cudaStream_t st);
 
 // ---- tcgen05 / TMEM / TMA GEMM (gemm_tc.cu), 16-bit (op16) operands, fp32 accumulate -----------------

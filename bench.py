@@ -457,6 +457,28 @@ def run_extras(torch, ab, synth, LogMel, enc, fe, pcm, args, pk, dev):
         out["ragged"] = {"what": "64 clips of 5 .. 30 s (uniform) padded to 30 s: default (padding encoded, as the reference) vs skip_padding",
                          "valid_audio_s": valid_s, "ms_padding_encoded": ms_pad, "ms_padding_skipped": ms_skip,
                          "valid_audio_s_per_s_skipped": valid_s / (ms_skip * 1e-3), "valid_audio_s_per_s_padded": valid_s / (ms_pad * 1e-3)}
+    # --- the attention + rotary block on encoded audio: fp32 CUDA-core variant, tensor-core variant,
+    #     and the tensor-core variant with the K|V of the audio computed once (what a decoder reuses)
+    try:
+        Ba = 16
+        xa = torch.randn(Ba, T, DIMS, device=dev)
+        res = {"what": f"attention(dims={DIMS}, head={HEAD}, n_type='rmsnorm') + rotary on {Ba} x {T} encoded frames (model.py:234-317)"}
+        for comp in ("fp32", "bf16"):
+            torch.manual_seed(1)
+            att = ab.AudioAttention(DIMS, HEAD, compute=comp)
+            res[comp + "_ms"] = timed_ms(torch, lambda: att(xa), 5 if comp == "fp32" else 20, 2)
+            if comp == "bf16":
+                kv = att.encode_kv(xa)
+                res["bf16_cached_kv_ms"] = timed_ms(torch, lambda: att(xa, kv=kv), 20, 2)
+                xq = torch.randn(Ba, 64, DIMS, device=dev)
+                res["bf16_cached_kv_64_queries_ms"] = timed_ms(torch, lambda: att(xq, kv=kv), 20, 2)
+                fl = Ba * T * (8.0 * DIMS * DIMS + 4.0 * T * DIMS)
+                res["bf16_tflops"] = fl / res["bf16_ms"] / 1e9
+            del att
+        out["attention_block"] = res
+        del xa
+    except Exception as e:
+        out["attention_block"] = {"unavailable": repr(e)[:200]}
     # --- BASELINE config 3: front end alone, 256 x 30 s
     pcm3 = synth.white_noise_batch(256, N, device=dev)
     sweep = []

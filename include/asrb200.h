@@ -185,7 +185,9 @@ int asrb_pcm_to_hidden_ragged(const asrb_logmel_plan* plan, asrb_encoder* enc,
 /* ------------------------------------------------------------------------------------
  * Secondary: the `attention` block's live branch applied to encoded audio
  * (model.py:234-317 with n_type="rmsnorm", xa=None, mask=None) including `rotary`
- * (model.py:171-214).  Batched = the reference's B=1 semantics per utterance.
+ * (model.py:171-214).  Batched = the reference's B=1 semantics per utterance (per-sample rotary magnitudes).
+ * compute = ASRB_F32 (CUDA cores, <= 1e-4) or ASRB_BF16 (tensor cores: tcgen05 projections + flash attention; dims % 128 == 0,
+ * head_dim 64 or 128).
  * Keys: q.0.weight q.1.weight q.1.bias kv.0.weight kv.1.weight kv.1.bias out.1.weight
  * out.1.bias ln.weight (c.* and rot.lin.* are unused by the live branch).
  * ---------------------------------------------------------------------------------- */
@@ -199,6 +201,20 @@ size_t asrb_attention_workspace_bytes(const asrb_attention* att, int64_t batch, 
 /* x, out: [batch][frames][dims] fp32 device */
 int asrb_attention_forward(asrb_attention* att, const float* x, int64_t batch, int64_t frames,
                            float* out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* K|V reuse (compute = ASRB_BF16 only).  The reference recomputes norm_kv -> Linear(D, 2D) -> rotary ->
+ * per-head RMSNorm of the encoded audio in every `residual` call (8 per decoder block, model.py:617-626) and for every
+ * generated token (model.py:691-699).  Here asrb_attention_encode_kv() does that once for xa [batch][kv_frames][dims] fp32 into a
+ * caller-owned cache of asrb_attention_kv_bytes() bytes (256-B aligned; K with rotary and norm applied | V, 16-bit), and
+ * asrb_attention_forward_cached() attends queries x [batch][q_frames][dims] (model.py:258-262 with xa given: rotary
+ * magnitudes of q from x, of k from xa; no mask) against it.  encode_kv(x) + forward_cached(x) == asrb_attention_forward(x).
+ * Workspace: asrb_attention_workspace_bytes(att, batch, frames of the call). */
+size_t asrb_attention_kv_bytes(const asrb_attention* att, int64_t batch, int64_t kv_frames);
+int asrb_attention_encode_kv(asrb_attention* att, const float* xa, int64_t batch, int64_t kv_frames, void* kv_cache,
+                             void* workspace, size_t workspace_bytes, void* stream);
+int asrb_attention_forward_cached(asrb_attention* att, const float* x, int64_t batch, int64_t q_frames,
+                                  const void* kv_cache, int64_t kv_frames, float* out,
+                                  void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Measurement aid (process-wide; off by default, not for production): between

@@ -46,20 +46,24 @@ def rotary_apply(x: torch.Tensor, xa: torch.Tensor) -> torch.Tensor:
     return torch.view_as_real(xc).flatten(-2).type_as(x)
 
 
-def attention_forward(sd: SD, x: torch.Tensor, head: int) -> torch.Tensor:
-    """``attention.forward`` live branch, ``x [B, T, D]`` -> ``[B, T, D]``."""
+def attention_forward(sd: SD, x: torch.Tensor, head: int, xa: torch.Tensor = None) -> torch.Tensor:
+    """``attention.forward`` live branch, ``x [B, T, D]`` -> ``[B, T, D]``.  With ``xa [B, Tk, D]`` the keys and values
+    come from ``xa`` (model.py:259: ``k, v = n.kv(aorb(xa, x))``) and the rotary magnitudes of ``k`` from ``xa``
+    (model.py:306); ``q`` keeps ``x`` for both."""
     B, T, D = x.shape
     hd = D // head
     scale = hd ** -0.25                                           # model.py:239
     outs = []
     for b in range(B):
         xb = x[b:b + 1]
-        kv = F.linear(_rms_norm(xb, sd["kv.0.weight"]), sd["kv.1.weight"], sd["kv.1.bias"])
-        k, v = kv.view(1, T, 2, head, hd).permute(2, 0, 3, 1, 4)  # 'b c (kv h d) -> kv b h c d'
+        ab = xb if xa is None else xa[b:b + 1]
+        Tk = ab.shape[1]
+        kv = F.linear(_rms_norm(ab, sd["kv.0.weight"]), sd["kv.1.weight"], sd["kv.1.bias"])
+        k, v = kv.view(1, Tk, 2, head, hd).permute(2, 0, 3, 1, 4)  # 'b c (kv h d) -> kv b h c d'
         q = F.linear(_rms_norm(xb, sd["q.0.weight"]), sd["q.1.weight"], sd["q.1.bias"])
         q = q.view(1, T, head, hd).transpose(1, 2)
         q = rotary_apply(q * scale, xb)                           # model.py:303-306
-        k = rotary_apply(k * scale, xb)
+        k = rotary_apply(k * scale, ab)
         qn, kn = _rms_norm(q, sd["ln.weight"]), _rms_norm(k, sd["ln.weight"])
         s = torch.matmul(qn, kn.transpose(-1, -2)) / math.sqrt(hd)   # SDPA default scale, :307
         a = torch.matmul(torch.softmax(s, dim=-1), v)

@@ -166,6 +166,15 @@ def main():
     assert d <= 2e-6, d
     att_gold["att_x"], att_gold["att_y"] = x.numpy(), ref.numpy()
     report["cases"]["attention_rotary"] = {"oracle_vs_ref_maxabs": d, "cfg": [D, H, T]}
+    # cross-attention against another sequence (keys / values and k's rotary magnitudes from xa, model.py:259, 306)
+    xa = torch.randn(2, 53, D, generator=g)
+    with torch.no_grad():
+        refx = torch.cat([att(x[b:b + 1], xa=xa[b:b + 1]) for b in range(2)])
+    oursx = oracle.attention_forward(sd, x, H, xa=xa)
+    dx = float((refx - oursx).abs().max())
+    assert dx <= 2e-6, dx
+    att_gold["att_xa"], att_gold["att_cross_y"] = xa.numpy(), refx.numpy()
+    report["cases"]["attention_rotary_cross"] = {"oracle_vs_ref_maxabs": dx, "cfg": [D, H, T, 53]}
     np.savez_compressed(os.path.join(GOLD, "attention.npz"), **att_gold)
 
     with open(os.path.join(GOLD, "PINNED.json"), "w") as f:

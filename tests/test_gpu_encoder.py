@@ -271,3 +271,30 @@ def test_ragged_batch_skips_padding_without_touching_valid_frames(ab, D, L, enc,
     for b in range(len(lengths)):
         v = int(frames[b])
         assert torch.equal(rag2[b, :v], base[b, :v]) and torch.all(rag2[b, v:] == 0), b
+
+
+@pytest.mark.parametrize("D,H,B,T", [(256, 4, 2, 301), (512, 4, 2, 1001), (256, 2, 1, 130)])
+def test_attention_block_on_tensor_cores_with_kv_reuse(ab, D, H, B, T):
+    """the attention + rotary block on tcgen05 (projections + flash attention), per-sample
+    rotary magnitudes, and the K|V of the attended sequence computed once and reused."""
+    sd = oracle.random_attention_state_dict(D, H, seed=12)
+    a = ab.AudioAttention(D, H, compute="bf16")
+    a.load_state_dict(sd)
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(B, T, D, generator=g)
+    ref = oracle.attention_forward(sd, x, H)
+    y = a(x.cuda())
+    err = (y.cpu() - ref).abs()
+    tol = 2e-2 + 1e-2 * ref.abs()
+    print(f"attention block TC D={D} H={H} T={T}: max-abs {float(err.max()):.4f}  worst err/tol {float((err / tol).max()):.3f}  refmax {float(ref.abs().max()):.2f}")
+    assert bool((err <= tol).all())
+    # self-attention through the cache == the one-call form, bit for bit
+    kv = a.encode_kv(x.cuda())
+    assert torch.equal(a(x.cuda(), kv=kv), y)
+    # cross-attention: shorter query sequences (decoder states) against the cached encoded audio, cache reused across calls
+    for Tq in (1, 17, 200):
+        xq = torch.randn(B, Tq, D, generator=g)
+        refx = oracle.attention_forward(sd, xq, H, xa=x)
+        yx = a(xq.cuda(), kv=kv).cpu()
+        e = (yx - refx).abs()
+        assert bool((e <= 2e-2 + 1e-2 * refx.abs()).all()), (Tq, float(e.max()))

@@ -99,6 +99,10 @@ def test_attention_matches_reference_fixture(golden):
     x = torch.from_numpy(golden["attention"]["att_x"])
     y = oracle.attention_forward(sd, x, 4)
     assert float((y - torch.from_numpy(golden["attention"]["att_y"])).abs().max()) <= 1e-5
+    # cross-attention (keys / values and k's rotary magnitudes from xa, model.py:259, 306)
+    xa = torch.from_numpy(golden["attention"]["att_xa"])
+    yx = oracle.attention_forward(sd, x, 4, xa=xa)
+    assert float((yx - torch.from_numpy(golden["attention"]["att_cross_y"])).abs().max()) <= 1e-5
 
 
 def test_encoder_param_count():
