@@ -43,6 +43,7 @@ struct LogmelParams {
     uint32_t* tile_min;        // [B * tiles_per_utt]: order-preserving image of each tile's smallest log10(mel) (the floor pass skips tiles above the floor)
     float* pool_out;           // optional [B][pool_target]: adaptive average pooling of the PCM (essentials.py:493-503)
     int64_t pool_target;
+    int a_bytes;               // shared-memory area A (see the kernel): max(partner exchange, staged PCM span + output staging tile)
 };
 
 template <int NFFT, int R, int FB, int HOP>
@@ -56,7 +57,10 @@ struct LogmelCfg {
     static constexpr int PP = FB + 4;                  // floats per power row (pitch 9 / 5 chunks of 16 B)
     static constexpr int P_ROWS = NB + 4;              // zero-weight padding taps read up to 3 rows past the last bin
     static constexpr int P_BYTES = P_ROWS * PP * 4;
-    static constexpr int REGION = Y_BYTES > E_BYTES + P_BYTES ? Y_BYTES : E_BYTES + P_BYTES;
+    // Shared-memory timeline of one tile (area A = the first a_bytes, run-time: >= E_BYTES and >= PCM span + staging tile):
+    //   PCM span (in A)  -> registers -> Y (transpose, A + beyond)  -> E (partner exchange, in A) | P (power rows, after A)
+    //   -> during the mel stage A is dead again: the NEXT tile's PCM span streams into it, next to the 16-bit output staging
+    __host__ __device__ static constexpr int region(int a_bytes) { return Y_BYTES > a_bytes + P_BYTES ? Y_BYTES : a_bytes + P_BYTES; }
     // hop = 160, R = 20: the four frames of a quad start 640 samples = 0 banks apart from the next quad, whose
     // first 12 threads share a warp with this quad's 20: a gap of 20 words per quad in the staged span puts them on
     // the 12 banks the first 20 leave free.  640 is a multiple of R, so which side of a gap a sample falls on is a
@@ -119,13 +123,12 @@ logmel_kernel(const LogmelParams p, int tiles_per_utt, int total_tiles) {
     const int span = (FB - 1) * hop + NFFT;
     const int span4 = (span + 3) & ~3;
     const int pcm_words = span4 + C::GAP * C::QUADS + 4;
-    // region: Y (transpose) | E (partner exchange) + P (power rows); E doubles as the fused path's output staging
     float4* s_y   = reinterpret_cast<float4*>(smem_raw);
     float4* s_e   = reinterpret_cast<float4*>(smem_raw);
-    float*  s_p   = reinterpret_cast<float*>(smem_raw + C::E_BYTES);
-    op16*   s_cl  = reinterpret_cast<op16*>(smem_raw);
-    float*  s_pcm = reinterpret_cast<float*>(smem_raw + C::REGION);            // [pcm_words]
-    float*  s_win = s_pcm + pcm_words;                                          // [NFFT]
+    float*  s_p   = reinterpret_cast<float*>(smem_raw + p.a_bytes);
+    float*  s_pcm = reinterpret_cast<float*>(smem_raw);                         // [pcm_words], area A
+    op16*   s_cl  = reinterpret_cast<op16*>(smem_raw + ((pcm_words * 4 + 15) & ~15));   // area A, behind the PCM span
+    float*  s_win = reinterpret_cast<float*>(smem_raw + C::region(p.a_bytes));  // [NFFT]
     float2* s_tw  = reinterpret_cast<float2*>(s_win + NFFT);                    // [R*R]
     float*  s_melw = reinterpret_cast<float*>(s_tw + R * R);                    // [M][kmax]
     int*    s_lo  = reinterpret_cast<int*>(s_melw + p.M * p.kmax);              // [M]
@@ -270,6 +273,7 @@ logmel_kernel(const LogmelParams p, int tiles_per_utt, int total_tiles) {
                 x[n1].re = vmul(w, make_float2(v[0], v[1]));
                 x[n1].im = vmul(w, make_float2(v[2], v[3]));
             }
+            __syncthreads();                                 // the PCM span is in registers everywhere: the transpose may overwrite it
             SmallDFT<R>::run(x);
             yq[j] = pack4(x[0]);
 #pragma unroll
@@ -278,8 +282,7 @@ logmel_kernel(const LogmelParams p, int tiles_per_utt, int total_tiles) {
                 yq[k1 * C::YP + j] = pack4(cmul_cs(x[k1], tw.x, tw.y));
             }
         }
-        __syncthreads();                                     // everyone is done with the PCM span, too:
-        { const int next = tile + gridDim.x; if (next < total_tiles) by_tma = prefetch(next); }
+        __syncthreads();
 
         // ---- round 2: thread k1 = j does the R-point DFT over n2 -> Z[j + R k2] ----
         cx2 z[R];
@@ -315,6 +318,9 @@ logmel_kernel(const LogmelParams p, int tiles_per_utt, int total_tiles) {
             }
         }
         __syncthreads();
+
+        // area A is dead until the next tile's transpose: the next PCM span streams into it under the mel stage
+        { const int next = tile + gridDim.x; if (next < total_tiles) by_tma = prefetch(next); }
 
         // ---- banded mel projection + log10 + (x+4)/4.  Work item = (filter m, frame quad): a thread keeps its quad and walks
         // the filters R apart; the 8 (4) lanes that share m read one power row per tap, conflict free, and the weights arrive
@@ -370,7 +376,7 @@ logmel_kernel(const LogmelParams p, int tiles_per_utt, int total_tiles) {
         vmax = warp_max(vmax);
         vmin = -warp_max(-vmin);
         if (lane == 0) { s_red[warp] = vmax; s_red[32 + warp] = vmin; }
-        __syncthreads();                                    // staging tile complete; P / E are free for the next tile
+        __syncthreads();                                    // staging tile complete; P is free for the next tile
         if (p.out_cl) {                                     // rows of CP 16-bit values, two per 32-bit word: a warp per frame
             const int wpr = p.CP >> 1, mw = (p.M + 1) >> 1; // words per row, words that hold real channels
             for (int fr = warp; fr < FB && t0 + fr < p.T; fr += nwarp) {
@@ -540,11 +546,12 @@ static int launch_logmel(const asrb_logmel_plan* pl, LogmelParams p, int64_t bat
     using C = LogmelCfg<NFFT, R, FB, HOP>;
     const int span = (FB - 1) * pl->hop + NFFT;
     const size_t pcm_words = ((span + 3) & ~3) + C::GAP * C::QUADS + 4;
-    size_t smem = C::REGION + sizeof(float) * (pcm_words + NFFT) + sizeof(float2) * (R * R) +
+    size_t a_bytes = ((pcm_words * 4 + 15) & ~(size_t)15) + (p.out_cl ? ((sizeof(op16) * FB * (p.CP + 2) + 15) & ~(size_t)15) : 0);
+    if (a_bytes < (size_t)C::E_BYTES) a_bytes = C::E_BYTES;
+    p.a_bytes = (int)a_bytes;
+    size_t smem = C::region((int)a_bytes) + sizeof(float) * NFFT + sizeof(float2) * (R * R) +
                   sizeof(float) * (size_t)pl->n_mels * pl->kmax + sizeof(int) * (2 * pl->n_mels);
-    if (smem > 227 * 1024) return fail(ASRB_E_ARG, "asrb_logmel_f32: hop/n_mels need %zu B of shared memory", smem);
-    if (p.out_cl && sizeof(op16) * FB * (p.CP + 2) > (size_t)C::E_BYTES)
-        return fail(ASRB_E_ARG, "log-mel: channels-last pitch %d does not fit the staging tile", p.CP);
+    if (smem > 227 * 1024) return fail(ASRB_E_ARG, "asrb_logmel_f32: hop/n_mels/channel pitch need %zu B of shared memory", smem);
     auto kern = logmel_kernel<NFFT, R, FB, HOP>;
     ASRB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 1;
