@@ -131,8 +131,7 @@ logmel_kernel(const LogmelParams p, int tiles_per_utt, int total_tiles) {
     float*  s_win = reinterpret_cast<float*>(smem_raw + C::region(p.a_bytes));  // [NFFT]
     float2* s_tw  = reinterpret_cast<float2*>(s_win + NFFT);                    // [R*R]
     float*  s_melw = reinterpret_cast<float*>(s_tw + R * R);                    // [M][kmax]
-    int*    s_lo  = reinterpret_cast<int*>(s_melw + p.M * p.kmax);              // [M]
-    int*    s_n4  = s_lo + p.M;                                                 // [M] taps / 4, rounded up
+    int2*   s_meta = reinterpret_cast<int2*>(s_melw + p.M * p.kmax);            // [M]: (first bin * row pitch, taps / 4 rounded up)
     __shared__ float s_red[64];
     __shared__ __align__(8) uint64_t s_bar;                                     // completion of the TMA-fetched PCM span
 
@@ -200,7 +199,7 @@ logmel_kernel(const LogmelParams p, int tiles_per_utt, int total_tiles) {
     for (int i = tid; i < NFFT; i += C::THREADS) s_win[i] = p.window[i];
     for (int i = tid; i < R * R; i += C::THREADS) s_tw[i] = p.twiddle[i];
     for (int i = tid; i < p.M * p.kmax; i += C::THREADS) s_melw[i] = p.mel_w[i];
-    for (int i = tid; i < p.M; i += C::THREADS) { s_lo[i] = p.mel_lo[i]; s_n4[i] = (p.mel_cnt[i] + 3) >> 2; }
+    for (int i = tid; i < p.M; i += C::THREADS) s_meta[i] = make_int2(p.mel_lo[i] * C::PP, (p.mel_cnt[i] + 3) >> 2);
     for (int i = tid; i < 4 * C::PP; i += C::THREADS) s_p[C::NB * C::PP + i] = 0.f;    // rows the zero-weight padding taps touch: finite
 
     const int q = tid / R, j = tid - q * R;                  // frame quad, position inside the FFT
@@ -332,10 +331,16 @@ logmel_kernel(const LogmelParams p, int tiles_per_utt, int total_tiles) {
             const int qq = tid & (C::QUADS - 1);
             const int tq = t0 + 4 * qq;                      // first frame of this thread's quad
             const bool full = t0 + FB <= Tb;                 // every frame of the tile is a frame of the utterance (Tb <= T)
-            for (int m = tid / C::QUADS; m < p.M; m += R) {
-                int n4 = s_n4[m];
-                const float4* w4 = reinterpret_cast<const float4*>(s_melw + m * p.kmax);
-                const float* px = s_p + s_lo[m] * C::PP + 4 * qq;
+            const int M = p.M, kmax4 = p.kmax >> 2, T = p.T;
+            const float* pq = s_p + 4 * qq;
+            const float4* wbase = reinterpret_cast<const float4*>(s_melw);
+            float* obase = p.out ? p.out + (int64_t)b * M * T + tq : nullptr;
+            op16* cbase = s_cl + (4 * qq) * clp;
+            for (int m = tid / C::QUADS; m < M; m += R) {
+                const int2 meta = s_meta[m];
+                int n4 = meta.y;
+                const float4* w4 = wbase + m * kmax4;
+                const float* px = pq + meta.x;
                 V2 a01 = make_float2(0.f, 0.f), a23 = make_float2(0.f, 0.f);
                 while (n4 > 0) {
                     if (n4 >= 3) mel_taps<3, C::PP>(px, w4, a01, a23);
@@ -351,11 +356,11 @@ logmel_kernel(const LogmelParams p, int tiles_per_utt, int total_tiles) {
                 if (full) {
                     vmax = fmaxf(vmax, fmaxf(fmaxf(lg[0], lg[1]), fmaxf(lg[2], lg[3])));
                     vmin = fminf(vmin, fminf(fminf(lg[0], lg[1]), fminf(lg[2], lg[3])));
-                    if (p.out_cl) {
+                    if (!obase) {
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) s_cl[(4 * qq + i) * clp + m] = to_op16(norm(lg[i]));
+                        for (int i = 0; i < 4; ++i) cbase[i * clp + m] = to_op16(norm(lg[i]));
                     } else {
-                        float* o = p.out + ((int64_t)b * p.M + m) * p.T + tq;
+                        float* o = obase + (int64_t)m * T;
 #pragma unroll
                         for (int i = 0; i < 4; ++i) o[i] = norm(lg[i]);
                     }
@@ -363,11 +368,11 @@ logmel_kernel(const LogmelParams p, int tiles_per_utt, int total_tiles) {
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const int t = tq + i;
-                        if (t < p.T) {
+                        if (t < T) {
                             float sv = 0.f;                                     // DataCollator pad value
                             if (t < Tb) { vmax = fmaxf(vmax, lg[i]); vmin = fminf(vmin, lg[i]); sv = norm(lg[i]); }
-                            if (p.out_cl) s_cl[(4 * qq + i) * clp + m] = to_op16(sv);
-                            else p.out[((int64_t)b * p.M + m) * p.T + t] = sv;
+                            if (!obase) cbase[i * clp + m] = to_op16(sv);
+                            else obase[(int64_t)m * T + i] = sv;
                         }
                     }
                 }
@@ -550,7 +555,7 @@ static int launch_logmel(const asrb_logmel_plan* pl, LogmelParams p, int64_t bat
     if (a_bytes < (size_t)C::E_BYTES) a_bytes = C::E_BYTES;
     p.a_bytes = (int)a_bytes;
     size_t smem = C::region((int)a_bytes) + sizeof(float) * NFFT + sizeof(float2) * (R * R) +
-                  sizeof(float) * (size_t)pl->n_mels * pl->kmax + sizeof(int) * (2 * pl->n_mels);
+                  sizeof(float) * (size_t)pl->n_mels * pl->kmax + sizeof(int2) * pl->n_mels;
     if (smem > 227 * 1024) return fail(ASRB_E_ARG, "asrb_logmel_f32: hop/n_mels/channel pitch need %zu B of shared memory", smem);
     auto kern = logmel_kernel<NFFT, R, FB, HOP>;
     ASRB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -184,7 +184,8 @@ class ShardedEncoder:
         # "peer": copy-engine pushes through symmetric memory (PeerExchange); "nccl": grouped send/recv;
         # "auto": peer on the NCCL backend when shape_of is known and the rendezvous succeeds, else nccl
         self.exchange = exchange
-        self.slots, self.multicast = slots, multicast
+        import os
+        self.slots, self.multicast = slots, multicast and os.environ.get("ASRB_MULTICAST", "1") != "0"
         self._peer: Optional[PeerExchange] = None
         self._peer_key = None
 
