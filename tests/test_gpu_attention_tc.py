@@ -25,9 +25,13 @@ def test_attention_tc_matches_torch(built_lib, B, T, D, H):
     op = built_lib.operand_dtype()
     qkv = (torch.randn(B, T, 3 * D, device="cuda", generator=g) * 1.5).to(op)
     qkv[..., :D] *= 2.0                                   # sharper softmax: the running max really moves
-    out = torch.full((B, T, D), float("nan"), device="cuda", dtype=op)
+    guard = 64 * D                                         # sentinel rows before and after: nothing may be written outside the tensor
+    buf = torch.full((B * T * D + 2 * guard,), 12345.0, device="cuda", dtype=op)
+    out = buf[guard: guard + B * T * D].view(B, T, D)
+    out.fill_(float("nan"))
     built_lib.check(lib.asrb_test_attention_tc(qkv.data_ptr(), out.data_ptr(), B, T, D, H, None), "asrb_test_attention_tc")
     torch.cuda.synchronize()
+    assert bool((buf[:guard] == 12345.0).all()) and bool((buf[-guard:] == 12345.0).all()), "wrote outside the output tensor"
     hd = D // H
     q, k, v = [t.float().view(B, T, H, hd).transpose(1, 2) for t in qkv.split(D, dim=-1)]
     s = (q @ k.transpose(-1, -2)) / math.sqrt(hd)
