@@ -6,9 +6,13 @@
 //   warp 0      TMA producer: Q once, then a 2-deep ring of K tiles and a 2-deep ring of V tiles
 //   warp 1      MMA issuer:   S_j = Q K_j^T (SS, both K-major)  ->  TMEM S[j&1] (128 fp32 columns)
 //                             O  += P_j V_j (A = P in smem K-major, B = V in smem MN-major) -> TMEM O
-//   warps 2..5  softmax:      thread = query row (TMEM lane); online softmax in the exp2 domain with
-//                             a stale running max (O is rescaled in TMEM only when the max grew by
-//                             more than 2^8), P_j -> op16 -> swizzled smem, final O / l -> out op16.
+//   warps 2..9  softmax:      two warps per TMEM lane quadrant; a thread is a query row (TMEM lane) and owns ONE 64-key half
+//                             of every key tile (kept in registers between the max and the exp pass); the two halves
+//                             swap their row maxima through shared memory (one named barrier per tile) and keep
+//                             separate row sums until the end.  Online softmax in the exp2 domain with a stale running
+//                             max (O is rescaled in TMEM only when the max grew by more than 2^8, each half rescaling its
+//                             half of the columns), P_j -> op16 -> swizzled smem, final O / l -> out op16.
+//                             (Round 1 had one warp per quadrant: 1.5 warps per scheduler, 37 % tensor-pipe active.)
 // S is never written to HBM; scores and probabilities live in TMEM / shared memory only.
 #include "tc_common.cuh"
 
@@ -20,7 +24,7 @@ template <int HD> struct AttnCfg {
     static constexpr int KV_BYTES = BM * HD * 2;                 // one K (or V) tile: 128 keys x HD
     static constexpr int P_BYTES = BM * BM * 2;                  // 128 queries x 128 keys, 16-bit
     static constexpr int SMEM = Q_BYTES + 4 * KV_BYTES + 2 * P_BYTES + 256;
-    static constexpr int THREADS = 192;
+    static constexpr int THREADS = 64 + 256;                     // TMA + MMA warps, 8 softmax warps
     static_assert(SMEM <= 227 * 1024, "shared memory budget");
 };
 
@@ -78,6 +82,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     auto p_ready = [&](int s) { return bar0 + 8u * (11 + s); };
     auto pv_done = [&](int s) { return bar0 + 8u * (13 + s); };
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+    __shared__ float s_xch[2][2][BM];                            // [tile parity][key half][query row]: row maxima, at the end row sums
 
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // provably warp-uniform role index
     const int q0 = blockIdx.x * BM, h = blockIdx.y, b = blockIdx.z;
@@ -91,7 +96,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         mbar_init(q_full, 1);
         for (int s = 0; s < 2; ++s) {
             mbar_init(k_full(s), 1); mbar_init(k_empty(s), 1); mbar_init(v_full(s), 1); mbar_init(v_empty(s), 1);
-            mbar_init(s_full(s), 1); mbar_init(p_ready(s), 128); mbar_init(pv_done(s), 1);
+            mbar_init(s_full(s), 1); mbar_init(p_ready(s), 256); mbar_init(pv_done(s), 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -164,31 +169,33 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         }
     } else {
         // ================================ softmax warps ===============================
-        const int quad = warp & 3;
+        const int quad = warp & 3;                                   // TMEM lane quadrant this warp may read
+        const int half = (warp - 2) >> 2;                            // which 64 keys of every 128-key tile
         const int r = quad * 32 + lane;                              // query row of this thread
         const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
-        float m_used = -INFINITY;                                    // max the exponents are taken against
-        float l = 0.f;
+        float m_used = -INFINITY;                                    // max the exponents are taken against (same in both halves)
+        float l = 0.f;                                               // this half's share of the row sum
         for (int j = 0; j < n_kv; ++j) {
             const int st = j & 1; const uint32_t ph = (uint32_t)(j >> 1) & 1u;
             mbar_wait(s_full(st), ph);
             tc_fence_after();
-            const uint32_t ts = tm_s + lane_off + (uint32_t)(st * BM);
-            const int kbase = j * BM;
-            const bool tail = kbase + BM > p.Tk;                     // keys >= Tk are padding: mask them
-            // ---- pass A: row max of the scaled scores ----
-            float mx = -INFINITY;
+            const uint32_t ts = tm_s + lane_off + (uint32_t)(st * BM + half * 64);
+            const int kbase = j * BM + half * 64;
+            // ---- pass A: this half's scores into registers, row max of the raw scores (the scale is positive) ----
+            float sc[64];
+            tmem_ld32(ts, *reinterpret_cast<float(*)[32]>(sc));
+            tmem_ld32(ts + 32, *reinterpret_cast<float(*)[32]>(sc + 32));
+            if (kbase + 64 > p.Tk) {                                 // keys >= Tk are padding: mask them
 #pragma unroll
-            for (int c = 0; c < BM; c += 32) {
-                float v[32];
-                tmem_ld32(ts + c, v);
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const float sv = (tail && kbase + c + i >= p.Tk) ? -INFINITY : v[i] * p.scale_log2;
-                    mx = fmaxf(mx, sv);
-                }
+                for (int i = 0; i < 64; ++i) if (kbase + i >= p.Tk) sc[i] = -INFINITY;
             }
-            // ---- rescale O only when the max grew by more than 2^8 (warp-uniform decision) ----
+            float mx = sc[0];
+#pragma unroll
+            for (int i = 1; i < 64; ++i) mx = fmaxf(mx, sc[i]);
+            s_xch[st][half][r] = mx;
+            epi_bar(1, 256);                                         // both halves of every row have published their max
+            mx = fmaxf(mx, s_xch[st][half ^ 1][r]) * p.scale_log2;
+            // ---- rescale O only when the max grew by more than 2^8 (warp-uniform decision, identical in both halves) ----
             const bool grow = mx > m_used + 8.0f;
             if (__any_sync(0xffffffffu, grow)) {
                 const float m_new = grow ? mx : m_used;
@@ -197,7 +204,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
                     mbar_wait(pv_done((j - 1) & 1), (uint32_t)((j - 1) >> 1) & 1u);     // O is quiescent
                     tc_fence_after();
 #pragma unroll
-                    for (int c = 0; c < HD; c += 32) {
+                    for (int c = half * (HD / 2); c < (half + 1) * (HD / 2); c += 32) {  // this half's columns of O
                         float o[32];
                         tmem_ld32(tm_o + lane_off + c, o);
 #pragma unroll
@@ -209,42 +216,34 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
                 l *= factor;
                 m_used = m_new;
             }
-            // ---- pass B: p = 2^(s - m_used), row sum, P -> op16 -> swizzled smem (A operand of P V) ----
+            // ---- pass B: p = 2^(s * scale - m_used), row sum, P -> op16 -> swizzled smem (A operand of P V) ----
             if (j >= 2) mbar_wait(pv_done(st), (uint32_t)((j - 2) >> 1) & 1u);          // P buffer st is free again
-            unsigned char* pbuf = s_p + st * C::P_BYTES;
+            unsigned char* sub = s_p + st * C::P_BYTES + half * (BM * 128) + r * 128;    // this half's 64-key sub-tile, row r
+            float rs = 0.f;
 #pragma unroll
-            for (int c = 0; c < BM; c += 32) {
-                float v[32];
-                tmem_ld32(ts + c, v);
-                float rs = 0.f;
+            for (int i = 0; i < 64; ++i) { sc[i] = ex2f(fmaf(sc[i], p.scale_log2, -m_used)); rs += sc[i]; }
+            l += rs;
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const float sv = (tail && kbase + c + i >= p.Tk) ? -INFINITY : v[i] * p.scale_log2;
-                    v[i] = ex2f(sv - m_used);
-                    rs += v[i];
-                }
-                l += rs;
-                unsigned char* sub = pbuf + (c >> 6) * (BM * 128) + r * 128;             // 64-key sub-tile, row r
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int chunk = ((c & 32) >> 3) + i;
-                    uint4 q;
-                    q.x = pack_op16x2(v[8 * i + 0], v[8 * i + 1]); q.y = pack_op16x2(v[8 * i + 2], v[8 * i + 3]);
-                    q.z = pack_op16x2(v[8 * i + 4], v[8 * i + 5]); q.w = pack_op16x2(v[8 * i + 6], v[8 * i + 7]);
-                    *reinterpret_cast<uint4*>(sub + ((chunk ^ (r & 7)) << 4)) = q;
-                }
+            for (int i = 0; i < 8; ++i) {
+                uint4 q;
+                q.x = pack_op16x2(sc[8 * i + 0], sc[8 * i + 1]); q.y = pack_op16x2(sc[8 * i + 2], sc[8 * i + 3]);
+                q.z = pack_op16x2(sc[8 * i + 4], sc[8 * i + 5]); q.w = pack_op16x2(sc[8 * i + 6], sc[8 * i + 7]);
+                *reinterpret_cast<uint4*>(sub + ((i ^ (r & 7)) << 4)) = q;
             }
             fence_async_smem();                                      // generic-proxy writes -> visible to the MMA (async proxy)
             tc_fence_before();
             mbar_arrive(p_ready(st));
         }
-        // ---- epilogue: O / l -> op16 -> out[b, q0 + r, h*HD ...] ----
+        // ---- epilogue: O / l -> op16 -> out[b, q0 + r, h*HD ...]; the halves add their row sums and split the columns ----
+        s_xch[n_kv & 1][half][r] = l;
+        epi_bar(1, 256);
+        l += s_xch[n_kv & 1][half ^ 1][r];
         mbar_wait(pv_done((n_kv - 1) & 1), (uint32_t)((n_kv - 1) >> 1) & 1u);
         tc_fence_after();
         const float inv = 1.0f / l;
         const int t = q0 + r;
 #pragma unroll
-        for (int c = 0; c < HD; c += 32) {
+        for (int c = half * (HD / 2); c < (half + 1) * (HD / 2); c += 32) {
             float o[32];
             tmem_ld32(tm_o + lane_off + c, o);
             if (t < p.Tq) {
