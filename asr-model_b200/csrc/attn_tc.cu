@@ -1,17 +1,22 @@
 // Flash-style softmax attention on tcgen05 / TMEM for the optional TransformerEncoderLayer
 // (model.py:138,163: nn.MultiheadAttention, no mask, non-causal, softmax(q k^T / sqrt(hd)) v).
 //
-// One CTA = one (utterance, head, 128-query tile).  qkv is the packed op16 (16-bit operand format, common.cuh) [B][T][3D] output of
+// One CTA = one (utterance, head, 128-query tile); two neighbouring query tiles form a CLUSTER that shares every K and V
+// tile: each CTA fetches half of it (64 keys) and TMA-multicasts it into both, so the L2 -> SM traffic of the kernel --
+// its bound at T = 3001: 9.4 GB per call when every CTA streams all of K and V on its own -- is halved.  qkv is the packed op16 (16-bit operand format, common.cuh) [B][T][3D] output of
 // the in_proj GEMM; Q, K and V tiles arrive by TMA (3-D map, OOB rows zero filled).
 //   warp 0      TMA producer: Q once, then a 2-deep ring of K tiles and a 2-deep ring of V tiles
 //   warp 1      MMA issuer:   S_j = Q K_j^T (SS, both K-major)  ->  TMEM S[j&1] (128 fp32 columns)
-//                             O  += P_j V_j (A = P in smem K-major, B = V in smem MN-major) -> TMEM O
+//                             O  += P_j V_j (A = P in TENSOR MEMORY, B = V in smem MN-major)  -> TMEM O
 //   warps 2..9  softmax:      two warps per TMEM lane quadrant; a thread is a query row (TMEM lane) and owns ONE 64-key half
 //                             of every key tile (kept in registers between the max and the exp pass); the two halves
 //                             swap their row maxima through shared memory (one named barrier per tile) and keep
 //                             separate row sums until the end.  Online softmax in the exp2 domain with a stale running
 //                             max (O is rescaled in TMEM only when the max grew by more than 2^8, each half rescaling its
-//                             half of the columns), P_j -> op16 -> swizzled smem, final O / l -> out op16.
+//                             half of the columns), P_j -> op16 -> TMEM (two keys per 32-bit column: the PV MMA takes its A operand straight from
+//                             tensor memory, so P never crosses shared memory, whose bandwidth -- 128-wide MMAs read their
+//                             operands at the full 128 B/clk while TMA refills the K / V rings -- is this kernel's bound),
+//                             final O / l -> out op16.
 //                             (Round 1 had one warp per quadrant: 1.5 warps per scheduler, 37 % tensor-pipe active.)
 // S is never written to HBM; scores and probabilities live in TMEM / shared memory only.
 #include "tc_common.cuh"
@@ -22,8 +27,7 @@ template <int HD> struct AttnCfg {
     static constexpr int SUB = HD / 64;                          // 64-column sub-tiles per head_dim
     static constexpr int Q_BYTES = BM * HD * 2;
     static constexpr int KV_BYTES = BM * HD * 2;                 // one K (or V) tile: 128 keys x HD
-    static constexpr int P_BYTES = BM * BM * 2;                  // 128 queries x 128 keys, 16-bit
-    static constexpr int SMEM = Q_BYTES + 4 * KV_BYTES + 2 * P_BYTES + 256;
+    static constexpr int SMEM = Q_BYTES + 4 * KV_BYTES + 256;
     static constexpr int THREADS = 64 + 256;                     // TMA + MMA warps, 8 softmax warps
     static_assert(SMEM <= 227 * 1024, "shared memory budget");
 };
@@ -55,6 +59,14 @@ __host__ __device__ constexpr uint32_t make_idesc_ex(int n, bool b_mn_major) {
     return (1u << 4) | (ASRB_OP16_IS_F16 ? 0u : ((1u << 7) | (1u << 10))) | ((b_mn_major ? 1u : 0u) << 16) | ((uint32_t)(n >> 3) << 17) |
            ((uint32_t)(BM >> 4) << 24);
 }
+// A operand from tensor memory (lane = row, two 16-bit K elements per column), B from a shared-memory descriptor
+__device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
 __device__ __forceinline__ float ex2f(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -63,14 +75,13 @@ __device__ __forceinline__ float ex2f(float x) {
 
 template <int HD>
 __global__ void __launch_bounds__(AttnCfg<HD>::THREADS, 1)
-attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv, const AttnParams p) {
+attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv, const AttnParams p) {   // map_kv: 64-key boxes
     using C = AttnCfg<HD>;
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* s_q = smem;                                   // [SUB][128][128 B]
     unsigned char* s_k = s_q + C::Q_BYTES;                       // [2][SUB][128][128 B]
     unsigned char* s_v = s_k + 2 * C::KV_BYTES;                  // [2][SUB][128][128 B]
-    unsigned char* s_p = s_v + 2 * C::KV_BYTES;                  // [2][2][128][128 B]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_p + 2 * C::P_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_v + 2 * C::KV_BYTES);
     const uint32_t bar0 = smem_u32(bars);
     // q_full, k_full[2], k_empty[2], v_full[2], v_empty[2], s_full[2], p_ready[2], pv_done[2]
     const uint32_t q_full = bar0;
@@ -95,7 +106,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     if (warp == 1 && lane == 0) {
         mbar_init(q_full, 1);
         for (int s = 0; s < 2; ++s) {
-            mbar_init(k_full(s), 1); mbar_init(k_empty(s), 1); mbar_init(v_full(s), 1); mbar_init(v_empty(s), 1);
+            // a K / V slot is half written by the peer CTA: it is free once BOTH CTAs' MMAs have consumed it
+            mbar_init(k_full(s), 1); mbar_init(k_empty(s), 2); mbar_init(v_full(s), 1); mbar_init(v_empty(s), 2);
             mbar_init(s_full(s), 1); mbar_init(p_ready(s), 256); mbar_init(pv_done(s), 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -105,11 +117,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
-    __syncthreads();
+    cluster_sync_all();                              // the peer's barriers are initialised before anyone multicasts into it
     tc_fence_after();
+    const uint32_t crank = cluster_ctarank();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t tm_s = tmem_base;                 // S[2]: columns [0, 256)
     const uint32_t tm_o = tmem_base + 256;           // O: columns [256, 256 + HD)
+    const uint32_t tm_p = tmem_base + 384;           // P[2]: 2 x 64 columns (128 keys x 16 bit per row)
 
     if (warp == 0) {
         // ================================ TMA producer ================================
@@ -121,12 +135,14 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
                 const int st = j & 1; const uint32_t ph = (uint32_t)(j >> 1) & 1u;
                 mbar_wait(k_empty(st), ph ^ 1);
                 mbar_expect_tx(k_full(st), C::KV_BYTES);
-                for (int s = 0; s < C::SUB; ++s)
-                    tma_load_3d(smem_u32(s_k + st * C::KV_BYTES + s * (BM * 128)), &map_kv, p.k_col0 + h * HD + s * 64, j * BM, b, k_full(st));
+                for (int s = 0; s < C::SUB; ++s)     // my 64 keys of the tile, delivered to both CTAs of the pair
+                    tma_load_3d_mc(smem_u32(s_k + st * C::KV_BYTES + s * (BM * 128)) + crank * (64 * 128), &map_kv,
+                                   p.k_col0 + h * HD + s * 64, j * BM + (int)crank * 64, b, k_full(st), (uint16_t)3);
                 mbar_wait(v_empty(st), ph ^ 1);
                 mbar_expect_tx(v_full(st), C::KV_BYTES);
                 for (int s = 0; s < C::SUB; ++s)
-                    tma_load_3d(smem_u32(s_v + st * C::KV_BYTES + s * (BM * 128)), &map_kv, p.v_col0 + h * HD + s * 64, j * BM, b, v_full(st));
+                    tma_load_3d_mc(smem_u32(s_v + st * C::KV_BYTES + s * (BM * 128)) + crank * (64 * 128), &map_kv,
+                                   p.v_col0 + h * HD + s * 64, j * BM + (int)crank * 64, b, v_full(st), (uint16_t)3);
             }
         }
     } else if (warp == 1) {
@@ -144,7 +160,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
                     tc_mma(tm_s + (uint32_t)(st * BM), make_smem_desc(smem_u32(s_q) + off),
                            make_smem_desc(smem_u32(s_k + st * C::KV_BYTES) + off), idesc_qk, (uint32_t)(kk != 0));
                 }
-                tc_commit(k_empty(st));
+                tc_commit_mc(k_empty(st), (uint16_t)3);
                 tc_commit(s_full(st));
             };
             mbar_wait(q_full, 0);
@@ -158,11 +174,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
                 tc_fence_after();
 #pragma unroll
                 for (int kk = 0; kk < BM / 16; ++kk) {                      // 128 keys = 8 MMAs of K = 16
-                    const uint64_t adesc = make_smem_desc(smem_u32(s_p + st * C::P_BYTES) + (uint32_t)((kk >> 2) * (BM * 128) + (kk & 3) * 32));
                     const uint64_t bdesc = make_smem_desc_mn(smem_u32(s_v + st * C::KV_BYTES) + (uint32_t)(kk * 16 * 128), BM * 128);
-                    tc_mma(tm_o, adesc, bdesc, idesc_pv, (uint32_t)((j | kk) != 0));
+                    tc_mma_ts(tm_o, tm_p + (uint32_t)(st * 64 + kk * 8), bdesc, idesc_pv, (uint32_t)((j | kk) != 0));
                 }
-                tc_commit(v_empty(st));
+                tc_commit_mc(v_empty(st), (uint16_t)3);
                 tc_commit(pv_done(st));
                 if (j + 2 < n_kv) issue_qk(j + 2);
             }
@@ -216,21 +231,17 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
                 l *= factor;
                 m_used = m_new;
             }
-            // ---- pass B: p = 2^(s * scale - m_used), row sum, P -> op16 -> swizzled smem (A operand of P V) ----
-            if (j >= 2) mbar_wait(pv_done(st), (uint32_t)((j - 2) >> 1) & 1u);          // P buffer st is free again
-            unsigned char* sub = s_p + st * C::P_BYTES + half * (BM * 128) + r * 128;    // this half's 64-key sub-tile, row r
+            // ---- pass B: p = 2^(s * scale - m_used), row sum, P -> op16 -> TMEM (A operand of P V: row = lane, two keys per column) ----
             float rs = 0.f;
 #pragma unroll
             for (int i = 0; i < 64; ++i) { sc[i] = ex2f(fmaf(sc[i], p.scale_log2, -m_used)); rs += sc[i]; }
             l += rs;
+            float pw[32];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                uint4 q;
-                q.x = pack_op16x2(sc[8 * i + 0], sc[8 * i + 1]); q.y = pack_op16x2(sc[8 * i + 2], sc[8 * i + 3]);
-                q.z = pack_op16x2(sc[8 * i + 4], sc[8 * i + 5]); q.w = pack_op16x2(sc[8 * i + 6], sc[8 * i + 7]);
-                *reinterpret_cast<uint4*>(sub + ((i ^ (r & 7)) << 4)) = q;
-            }
-            fence_async_smem();                                      // generic-proxy writes -> visible to the MMA (async proxy)
+            for (int i = 0; i < 32; ++i) pw[i] = __uint_as_float(pack_op16x2(sc[2 * i], sc[2 * i + 1]));
+            if (j >= 2) mbar_wait(pv_done(st), (uint32_t)((j - 2) >> 1) & 1u);          // P buffer st is free again
+            tc_fence_after();
+            tmem_st32(tm_p + lane_off + (uint32_t)(st * 64 + half * 32), pw);
             tc_fence_before();
             mbar_arrive(p_ready(st));
         }
@@ -260,7 +271,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     }
 
     tc_fence_before();
-    __syncthreads();
+    cluster_sync_all();                              // no CTA exits while its peer may still write to it
     if (warp == 2) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
@@ -276,8 +287,16 @@ template <int HD>
 static int launch_attn(const CUtensorMap& mq, const CUtensorMap& mkv, const AttnParams& p, int64_t B, cudaStream_t st) {
     auto kern = attn_tc_kernel<HD>;
     ASRB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<HD>::SMEM));
-    dim3 grid((unsigned)((p.Tq + BM - 1) / BM), (unsigned)p.H, (unsigned)B);
-    kern<<<grid, AttnCfg<HD>::THREADS, AttnCfg<HD>::SMEM, st>>>(mq, mkv, p);
+    const unsigned q_tiles = (unsigned)((p.Tq + BM - 1) / BM);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((q_tiles + 1) & ~1u, (unsigned)p.H, (unsigned)B);   // pairs of query tiles (an odd last tile gets an idle partner that still loads its half)
+    cfg.blockDim = dim3(AttnCfg<HD>::THREADS);
+    cfg.dynamicSmemBytes = AttnCfg<HD>::SMEM; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    ASRB_CUDA(cudaLaunchKernelEx(&cfg, kern, mq, mkv, p));
     ASRB_LAUNCH_CHECK();
     return ASRB_OK;
 }
@@ -292,7 +311,7 @@ int launch_attention_tc_ex(const void* q, int ldq, int q_col0, const void* kv, i
     if (B > 65535) return fail(ASRB_E_ARG, "tcgen05 attention: batch %lld > 65535", (long long)B);
     CUtensorMap mq, mkv;
     ASRB_TRY(make_act_map(&mq, q, B, Tq, ldq));
-    ASRB_TRY(make_act_map(&mkv, kv, B, Tk, ldkv));
+    ASRB_TRY(make_act_map(&mkv, kv, B, Tk, ldkv, BM / 2));              // 64-key boxes: each CTA of a pair loads half a tile
     AttnParams p;
     p.Tq = (int)Tq; p.Tk = (int)Tk; p.D = D; p.H = H; p.n_kv = (int)((Tk + BM - 1) / BM);
     p.q_col0 = q_col0; p.k_col0 = k_col0; p.v_col0 = v_col0;
