@@ -137,7 +137,7 @@ logmel_kernel(const LogmelParams p, int tiles_per_utt, int total_tiles) {
 
     const int tid = threadIdx.x;
     const bool vec_ok = ((p.stride & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.pcm) & 15) == 0) && ((hop & 3) == 0);
-    const int clp = p.CP + 2;                                // staging pitch in 16-bit words: odd word count, conflict-free transposed writes
+    const int clp = p.CP + 4;                                // staging pitch in 16-bit words: rows stay 8-byte aligned, transposed writes 2-way conflicted at worst
 
     auto pos = [&](int s) { return C::SKEW ? s + C::GAP * (s / (4 * 160)) : s; };       // span index -> shared-memory word
     // Async copy of one tile's PCM span; everything past the utterance (and before sample 0) is zero filled.  All index
@@ -342,12 +342,10 @@ logmel_kernel(const LogmelParams p, int tiles_per_utt, int total_tiles) {
                 const float4* w4 = wbase + m * kmax4;
                 const float* px = pq + meta.x;
                 V2 a01 = make_float2(0.f, 0.f), a23 = make_float2(0.f, 0.f);
-                while (n4 > 0) {
-                    if (n4 >= 3) mel_taps<3, C::PP>(px, w4, a01, a23);
-                    else if (n4 == 2) mel_taps<2, C::PP>(px, w4, a01, a23);
-                    else mel_taps<1, C::PP>(px, w4, a01, a23);
-                    n4 -= 3; w4 += 3; px += 12 * C::PP;
-                }
+                while (n4 > 3) { mel_taps<3, C::PP>(px, w4, a01, a23); n4 -= 3; w4 += 3; px += 12 * C::PP; }
+                if (n4 == 3) mel_taps<3, C::PP>(px, w4, a01, a23);
+                else if (n4 == 2) mel_taps<2, C::PP>(px, w4, a01, a23);
+                else if (n4 == 1) mel_taps<1, C::PP>(px, w4, a01, a23);
                 float lg[4] = {a01.x, a01.y, a23.x, a23.y};
 #pragma unroll
                 for (int i = 0; i < 4; ++i)                  // MUFU lg2 (abs error ~2^-22); the argument is >= 1e-10: never denormal
@@ -382,18 +380,22 @@ logmel_kernel(const LogmelParams p, int tiles_per_utt, int total_tiles) {
         vmin = -warp_max(-vmin);
         if (lane == 0) { s_red[warp] = vmax; s_red[32 + warp] = vmin; }
         __syncthreads();                                    // staging tile complete; P is free for the next tile
-        if (p.out_cl) {                                     // rows of CP 16-bit values, two per 32-bit word: a warp per frame
-            const int wpr = p.CP >> 1, mw = (p.M + 1) >> 1; // words per row, words that hold real channels
-            for (int fr = warp; fr < FB && t0 + fr < p.T; fr += nwarp) {
-                uint32_t* dst = reinterpret_cast<uint32_t*>(p.out_cl + ((int64_t)b * p.T + t0 + fr) * p.CP);
-                const op16* srow = s_cl + fr * clp;
-                for (int w = lane; w < wpr; w += 32) {
-                    uint32_t v = 0u;                       // channels >= M: zero
-                    if (w < mw) {
-                        v = *reinterpret_cast<const uint32_t*>(srow + 2 * w);
-                        if (2 * w + 1 >= p.M) v &= 0xffffu;
-                    }
-                    dst[w] = v;
+        if (p.out_cl) {                                     // rows of CP 16-bit values leave as 8-byte words: at CP = 128 a warp moves one frame per load / store pair
+            const int dpr = p.CP >> 2, M = p.M;             // 8-byte words per row
+            const int nrows = min(FB, p.T - t0);
+            uint2* dst = reinterpret_cast<uint2*>(p.out_cl + ((int64_t)b * p.T + t0) * p.CP);
+            const uint2* src = reinterpret_cast<const uint2*>(s_cl);
+            const int spitch = clp >> 2;
+            for (int w = lane; w < dpr; w += 32) {
+                // channels 4w .. 4w+3: keep the real ones, the rest (>= M) are zero
+                const int c0 = 4 * w;
+                const uint32_t k0 = c0 + 1 < M ? 0xffffffffu : (c0 < M ? 0xffffu : 0u);
+                const uint32_t k1 = c0 + 3 < M ? 0xffffffffu : (c0 + 2 < M ? 0xffffu : 0u);
+                const int ws = c0 < M ? w : 0;              // always a staged word
+#pragma unroll 2
+                for (int fr = warp; fr < nrows; fr += nwarp) {
+                    const uint2 v = src[fr * spitch + ws];
+                    dst[(int64_t)fr * dpr + w] = make_uint2(v.x & k0, v.y & k1);
                 }
             }
         }
@@ -551,7 +553,7 @@ static int launch_logmel(const asrb_logmel_plan* pl, LogmelParams p, int64_t bat
     using C = LogmelCfg<NFFT, R, FB, HOP>;
     const int span = (FB - 1) * pl->hop + NFFT;
     const size_t pcm_words = ((span + 3) & ~3) + C::GAP * C::QUADS + 4;
-    size_t a_bytes = ((pcm_words * 4 + 15) & ~(size_t)15) + (p.out_cl ? ((sizeof(op16) * FB * (p.CP + 2) + 15) & ~(size_t)15) : 0);
+    size_t a_bytes = ((pcm_words * 4 + 15) & ~(size_t)15) + (p.out_cl ? ((sizeof(op16) * FB * (p.CP + 4) + 15) & ~(size_t)15) : 0);
     if (a_bytes < (size_t)C::E_BYTES) a_bytes = C::E_BYTES;
     p.a_bytes = (int)a_bytes;
     size_t smem = C::region((int)a_bytes) + sizeof(float) * NFFT + sizeof(float2) * (R * R) +
