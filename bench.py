@@ -265,11 +265,22 @@ def main():
     clocks = sampler.stop()
     ms_step = all_max(rank_ms)
     value = B * world * SECS / (ms_step * 1e-3)
-    per_rank_ms = [rank_ms]
+    per_rank_ms, exchange = [rank_ms], None
     if world > 1:
-        g = [torch.zeros(1, device=dev) for _ in range(world)]
-        dist.all_gather(g, torch.tensor([rank_ms], device=dev))
-        per_rank_ms = [float(x.item()) for x in g]
+        # the same K steps without the exchange (every rank on its own): what the gather costs on top of the compute
+        e0.record()
+        for _ in range(args.steps):
+            hot(pcm)
+        e1.record()
+        sync()
+        alone_ms = e0.elapsed_time(e1) / args.steps
+        g = [torch.zeros(2, device=dev) for _ in range(world)]
+        dist.all_gather(g, torch.tensor([rank_ms, alone_ms], device=dev))
+        per_rank_ms = [float(x[0].item()) for x in g]
+        alone = [float(x[1].item()) for x in g]
+        exchange = {"per_rank_ms_per_step_without_exchange": alone,
+                    "exposed_ms_per_step": ms_step - max(alone),
+                    "note": "step time with the gather minus the same ranks' step time with nobody exchanging (max over ranks each)"}
 
     # ---- end to end from pinned host memory through the public API ----
     # Every step: H2D of that step's PCM (pinned -> device, copy stream) + the fused forward + D2H of the FULL result
@@ -419,6 +430,8 @@ def main():
             "clocks": clocks, "roofline": roof, "gemm_family": gemm_family, "front_end": front_end, "cpu_baseline": cpu,
             "kernels": kernels, "whole_step": whole, "per_rank_ms_per_step": per_rank_ms,
         }
+        if exchange is not None:
+            line["exchange"] = exchange
         line.update(extras)
         if strong is not None:
             line["strong_scaling"] = strong
