@@ -6,7 +6,8 @@ Public surface (mirrors the reference):
   extract_features(batch, tokenizer, spectrogram=True, ...)   per-utterance drop-in
   AudioEncoder(mels, dims, head, layer, act, n_type, norm=False, enc=False)
                                           model.py:120-169, same state_dict keys
-  AudioAttention(dims, head)             model.py:234-317 live branch (secondary)
+  AudioAttention(dims, head)             model.py:234-317 live branch (secondary), K|V cache of the encoded audio
+  ResidualMLP(dims, num_types)           model.py:573-574 residual.mlp (tgate + Linear-GELU-Linear between one shared RMSNorm)
   ShardedEncoder / gather_outputs        utterance-sharded multi-GPU driver
 
 Everything numeric runs in hand-written CUDA behind the C ABI of
@@ -19,7 +20,7 @@ __version__ = "0.1.0"
 
 _LAZY = {
     "log_mel": "frontend", "extract_features": "frontend", "LogMel": "frontend", "waveform_feature": "frontend",
-    "AudioEncoder": "encoder", "AudioAttention": "attention",
+    "AudioEncoder": "encoder", "AudioAttention": "attention", "ResidualMLP": "attention",
     "ShardedEncoder": "sharded", "gather_outputs": "sharded", "shard_range": "sharded",
     "lib": "_lib", "synth": "synth",
 }

@@ -54,6 +54,10 @@ SYMBOLS = {
     "asrb_attention_kv_bytes": (_sz, [_vp, _i64, _i64]),
     "asrb_attention_encode_kv": (_int, [_vp, _vp, _i64, _i64, _vp, _vp, _sz, _vp]),
     "asrb_attention_forward_cached": (_int, [_vp, _vp, _i64, _i64, _vp, _i64, _vp, _vp, _sz, _vp]),
+    "asrb_mlp_create": (_int, [_i32, _i32, _int, C.POINTER(C.c_char_p), _pp, C.POINTER(_i64), _pp]),
+    "asrb_mlp_destroy": (None, [_vp]),
+    "asrb_mlp_workspace_bytes": (_sz, [_vp, _i64, _i64]),
+    "asrb_mlp_forward": (_int, [_vp, _vp, _i64, _i64, _int, _vp, _vp, _sz, _vp]),
     "asrb_profile_begin": (_int, []),
     "asrb_profile_end": (_int, []),
     "asrb_profile_get": (_int, [_int, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.POINTER(C.c_double),

@@ -119,3 +119,70 @@ class AudioAttention(nn.Module):
                                                                    out.data_ptr(), ws.data_ptr(), ws.numel(), _lib.stream_ptr()),
                            "asrb_attention_forward_cached")
         return out
+
+
+class _TGate(nn.Module):                                # parameter names of model.py:525-530
+    def __init__(self, dims, num_types):
+        super().__init__()
+        self.ga = nn.ModuleList([nn.Sequential(nn.Linear(dims, dims), nn.Identity()) for _ in range(num_types)])
+        self.cs = nn.Sequential(nn.Linear(dims, num_types), nn.Identity())
+
+
+class ResidualMLP(nn.Module):
+    """``residual.mlp`` of the reference applied to encoded audio (model.py:573-574, 583): shared RMSNorm -> ``tgate`` ->
+    ``Linear(D, n D)`` -> GELU -> ``Linear(n D, D)`` -> the same RMSNorm, on the tensor cores.  Parameter names are those of a
+    reference ``residual`` module (``ln.weight``, ``mlp.1.ga.i.0.weight``, ``mlp.1.cs.0.weight``, ``mlp.2.weight``,
+    ``mlp.4.weight``, ...), so ``load_state_dict(residual.state_dict(), strict=False)`` picks them up.
+    ``forward(x, add_residual=True)`` returns ``x + mlp(x)`` like ``residual.forward``'s last line."""
+
+    def __init__(self, dims: int, num_types: int = 3, act: str = "gelu"):
+        super().__init__()
+        if act != "gelu":
+            raise NotImplementedError("only act='gelu' (the reference configuration)")
+        self.dims, self.num_types = dims, num_types
+        self.ln = nn.RMSNorm(dims)
+        self.mlp = nn.Sequential(nn.Identity(), _TGate(dims, num_types), nn.Linear(dims, dims * num_types), nn.Identity(),
+                                 nn.Linear(dims * num_types, dims), nn.Identity())
+        self._handle, self._ws, self._lib = None, None, None
+
+    def _release(self):
+        if self._handle is not None:
+            self._lib.asrb_mlp_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self._release()
+        except Exception:
+            pass
+
+    def load_state_dict(self, state_dict, strict=True, assign=False):
+        own = set(self.state_dict())
+        r = super().load_state_dict({k: v for k, v in state_dict.items() if k in own}, strict=strict, assign=assign)
+        self._release() if self._lib is not None else None
+        return r
+
+    def prepare(self):
+        self._lib = _lib.load()
+        self._release()
+        n, names, ptrs, nums, keep = _lib.state_dict_arrays(dict(self.state_dict()))
+        h = C.c_void_p()
+        _lib.check(self._lib.asrb_mlp_create(self.dims, self.num_types, n, names, ptrs, nums, C.byref(h)), "asrb_mlp_create")
+        self._handle = h
+        return self
+
+    def forward(self, x: torch.Tensor, add_residual: bool = False) -> torch.Tensor:
+        if not x.is_cuda:
+            raise _lib.AsrbError("ResidualMLP needs a CUDA tensor: there is no CPU path")
+        x = x.float().contiguous()
+        B, T, D = x.shape
+        with torch.cuda.device(x.device):
+            if self._handle is None:
+                self.prepare()
+            out = torch.empty_like(x)
+            need = self._lib.asrb_mlp_workspace_bytes(self._handle, B, T)
+            if self._ws is None or self._ws.numel() < need or self._ws.device != x.device:
+                self._ws = torch.empty(max(need, 256), dtype=torch.uint8, device=x.device)
+            _lib.check(self._lib.asrb_mlp_forward(self._handle, x.data_ptr(), B, T, int(add_residual), out.data_ptr(),
+                                                  self._ws.data_ptr(), self._ws.numel(), _lib.stream_ptr()), "asrb_mlp_forward")
+        return out

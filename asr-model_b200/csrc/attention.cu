@@ -13,6 +13,7 @@
 #include <string>
 #include <vector>
 #include <cmath>
+#include <cstring>
 
 using namespace asrb;
 
@@ -203,4 +204,119 @@ extern "C" int asrb_attention_forward(asrb_attention* a, const float* x, int64_t
     ASRB_TRY(launch_rotary_headnorm(kv, DT_F32, 2 * D, x, a->ln_w, a->freqs, B, T, D, H, pre, st));  // k = first D columns
     ASRB_TRY(launch_attention_simt_ex(q, kv, kv + D, D, 2 * D, 2 * D, att, DT_F32, B, T, D, H, 1.0f / sqrtf((float)hd), st));
     return launch_gemm_simt(att, DT_F32, a->out_w, a->out_b, nullptr, out, DT_F32, B, T, D, D, 1, ACT_NONE, st);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// residual.mlp (model.py:573-574, 583): ln -> tgate -> Linear(D, n D) -> GELU -> Linear(n D, D) -> ln with ONE shared RMSNorm,
+// on the tensor cores: RMSNorm -> 16-bit operand; ONE GEMM for the n gate projections and the selector logits
+// ([n D + n] rows, zero-padded to a multiple of 128); softmax-weighted sigmoid gates (CUDA cores, one warp per row);
+// Linear + GELU epilogue; Linear -> fp32; RMSNorm (+ residual).
+// ------------------------------------------------------------------------------------------------------------------
+struct asrb_mlp {
+    int dims, n_types, n_gate;                          // n_gate = rows of the fused gate / selector weight (multiple of 128)
+    std::vector<void*> owned;
+    float *ln_w, *gate_b, *b1, *b2;
+    op16 *gate_w, *w1, *w2;
+};
+
+extern "C" int asrb_mlp_create(int32_t dims, int32_t n_types, int n_tensors, const char* const* names,
+                               const float* const* host_data, const int64_t* numels, asrb_mlp** out) {
+    if (!out || dims <= 0 || dims % 128 || n_types < 1 || n_types > 8) return fail(ASRB_E_ARG, "asrb_mlp_create: dims %% 128 == 0, 1 <= n_types <= 8");
+    ASRB_TRY(require_sm100());
+    std::map<std::string, std::pair<const float*, int64_t>> t;
+    for (int i = 0; i < n_tensors; ++i) t[names[i]] = {host_data[i], numels[i]};
+    auto get = [&](const std::string& key, int64_t n) -> const float* {
+        auto it = t.find(key);
+        if (it == t.end() || it->second.second != n) { fail(ASRB_E_WEIGHTS, "mlp tensor '%s' missing or misshaped", key.c_str()); return nullptr; }
+        return it->second.first;
+    };
+    asrb_mlp* m = new asrb_mlp();
+    m->dims = dims; m->n_types = n_types;
+    const int64_t D = dims, nD = (int64_t)n_types * D;
+    m->n_gate = (int)((nD + n_types + 127) / 128 * 128);
+    auto up = [&](const void* src, size_t bytes, void** dst) -> int {
+        void* p = nullptr;
+        ASRB_CUDA(cudaMalloc(&p, bytes));
+        m->owned.push_back(p);
+        ASRB_CUDA(cudaMemcpy(p, src, bytes, cudaMemcpyHostToDevice));
+        *dst = p;
+        return ASRB_OK;
+    };
+    auto half = [](const float* w, size_t n) { std::vector<op16> h(n); for (size_t i = 0; i < n; ++i) h[i] = host_to_op16(w[i]); return h; };
+    int r = ASRB_OK;
+    std::vector<float> gw((size_t)m->n_gate * D, 0.f), gb((size_t)m->n_gate, 0.f);
+    for (int i = 0; i < n_types && r == ASRB_OK; ++i) {
+        const std::string k = "mlp.1.ga." + std::to_string(i) + ".0.";
+        const float* w = get(k + "weight", D * D); const float* b = get(k + "bias", D);
+        if (!w || !b) { r = ASRB_E_WEIGHTS; break; }
+        memcpy(&gw[(size_t)i * D * D], w, sizeof(float) * D * D);
+        memcpy(&gb[(size_t)i * D], b, sizeof(float) * D);
+    }
+    const float *ln = nullptr, *csw = nullptr, *csb = nullptr, *w1 = nullptr, *b1 = nullptr, *w2 = nullptr, *b2 = nullptr;
+    if (r == ASRB_OK) {
+        ln = get("ln.weight", D); csw = get("mlp.1.cs.0.weight", (int64_t)n_types * D); csb = get("mlp.1.cs.0.bias", n_types);
+        w1 = get("mlp.2.weight", nD * D); b1 = get("mlp.2.bias", nD); w2 = get("mlp.4.weight", D * nD); b2 = get("mlp.4.bias", D);
+        if (!ln || !csw || !csb || !w1 || !b1 || !w2 || !b2) r = ASRB_E_WEIGHTS;
+    }
+    if (r == ASRB_OK) {
+        memcpy(&gw[(size_t)nD * D], csw, sizeof(float) * n_types * D);
+        memcpy(&gb[(size_t)nD], csb, sizeof(float) * n_types);
+        auto gh = half(gw.data(), gw.size()); auto h1 = half(w1, (size_t)nD * D); auto h2 = half(w2, (size_t)D * nD);
+        r = up(gh.data(), gh.size() * sizeof(op16), (void**)&m->gate_w);
+        if (!r) r = up(h1.data(), h1.size() * sizeof(op16), (void**)&m->w1);
+        if (!r) r = up(h2.data(), h2.size() * sizeof(op16), (void**)&m->w2);
+        if (!r) r = up(gb.data(), gb.size() * sizeof(float), (void**)&m->gate_b);
+        if (!r) r = up(b1, sizeof(float) * nD, (void**)&m->b1);
+        if (!r) r = up(b2, sizeof(float) * D, (void**)&m->b2);
+        if (!r) r = up(ln, sizeof(float) * D, (void**)&m->ln_w);
+    }
+    if (r != ASRB_OK) { asrb_mlp_destroy(m); return r; }
+    *out = m;
+    return ASRB_OK;
+}
+
+extern "C" void asrb_mlp_destroy(asrb_mlp* m) {
+    if (!m) return;
+    for (void* p : m->owned) cudaFree(p);
+    delete m;
+}
+
+extern "C" size_t asrb_mlp_workspace_bytes(const asrb_mlp* m, int64_t B, int64_t T) {
+    if (!m || B < 0 || T < 0) return 0;
+    const size_t rows = (size_t)B * T, D = m->dims;
+    return align_up(rows * D * 2, 256) * 2 + align_up(rows * (size_t)m->n_gate * 2, 256) + align_up(rows * D * m->n_types * 2, 256) +
+           align_up(rows * D * 4, 256) + 256;
+}
+
+extern "C" int asrb_mlp_forward(asrb_mlp* m, const float* x, int64_t B, int64_t T, int add_residual, float* out, void* ws,
+                                size_t ws_bytes, void* stream) {
+    if (!m) return fail(ASRB_E_ARG, "asrb_mlp_forward: NULL handle");
+    if (B < 0 || T < 0 || B > 65535) return fail(ASRB_E_ARG, "asrb_mlp_forward: bad shape");
+    if (B == 0 || T == 0) return ASRB_OK;
+    if (!x || !out) return fail(ASRB_E_ARG, "asrb_mlp_forward: NULL tensor");
+    if (!ws || ws_bytes < asrb_mlp_workspace_bytes(m, B, T) || ((uintptr_t)ws & 255))
+        return fail(ASRB_E_WORKSPACE, "asrb_mlp_forward: workspace NULL, misaligned or too small");
+    ASRB_TRY(require_sm100());
+    cudaStream_t st = (cudaStream_t)stream;
+    const int D = m->dims, nt = m->n_types;
+    const int64_t rows = B * T;
+    Arena ar(ws, ws_bytes);
+    op16* xn = ar.take<op16>(rows * D); op16* tg = ar.take<op16>(rows * D);
+    op16* g = ar.take<op16>(rows * (size_t)m->n_gate); op16* h = ar.take<op16>(rows * (size_t)D * nt);
+    float* y = ar.take<float>(rows * D);
+    ASRB_TRY(launch_rmsnorm(x, m->ln_w, xn, DT_OP16, rows, D, st));
+    TcGemmArgs a{};
+    a.A = xn; a.W = m->gate_w; a.bias = m->gate_b; a.out = g;
+    a.B = B; a.T = T; a.K = D; a.N = m->n_gate; a.taps = 1; a.epilogue = TC_BIAS_ACT; a.act = ACT_NONE;
+    ASRB_TRY(launch_gemm_tc(a, st));
+    ASRB_TRY(launch_tgate_combine(g, m->n_gate, tg, rows, D, nt, st));
+    TcGemmArgs l1{};
+    l1.A = tg; l1.W = m->w1; l1.bias = m->b1; l1.out = h;
+    l1.B = B; l1.T = T; l1.K = D; l1.N = D * nt; l1.taps = 1; l1.epilogue = TC_BIAS_ACT; l1.act = ACT_GELU;
+    ASRB_TRY(launch_gemm_tc(l1, st));
+    TcGemmArgs l2{};
+    l2.A = h; l2.W = m->w2; l2.bias = m->b2; l2.out = y; l2.out_f32 = 1;
+    l2.B = B; l2.T = T; l2.K = D * nt; l2.N = D; l2.taps = 1; l2.epilogue = TC_BIAS_ACT; l2.act = ACT_NONE;
+    ASRB_TRY(launch_gemm_tc(l2, st));
+    return launch_rmsnorm(y, m->ln_w, out, DT_F32, rows, D, st, add_residual ? x : nullptr);
 }

@@ -453,21 +453,47 @@ int launch_attention_simt(const void* qkv, void* out, DType dt, int64_t B, int64
 // ------------------------------------------------------------------------------------------
 template <class TO>
 __global__ void rmsnorm_kernel(const float* __restrict__ x, const float* __restrict__ w, TO* __restrict__ out,
-                               int64_t rows, int D, float eps) {
+                               int64_t rows, int D, float eps, const float* __restrict__ res) {
     const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) return;
     const int lane = threadIdx.x & 31;
     float s = 0.f;
     for (int c = lane; c < D; c += 32) { const float v = x[row * D + c]; s = fmaf(v, v, s); }
     const float r = rsqrtf(warp_sum(s) / (float)D + eps);
-    for (int c = lane; c < D; c += 32) io<TO>::st(out + row * D + c, x[row * D + c] * r * w[c]);
+    for (int c = lane; c < D; c += 32)
+        io<TO>::st(out + row * D + c, x[row * D + c] * r * w[c] + (res ? res[row * D + c] : 0.f));
 }
 
-int launch_rmsnorm(const float* x, const float* w, void* out, DType o_dt, int64_t rows, int D, cudaStream_t st) {
+int launch_rmsnorm(const float* x, const float* w, void* out, DType o_dt, int64_t rows, int D, cudaStream_t st, const float* res) {
     ProfScope ps("rmsnorm", st, 0.0, (double)rows * D * (o_dt == DT_F32 ? 8.0 : 6.0));
     const unsigned grid = (unsigned)((rows + 7) / 8);
-    if (o_dt == DT_F32) rmsnorm_kernel<float><<<grid, 256, 0, st>>>(x, w, (float*)out, rows, D, 1.1920928955078125e-07f);
-    else rmsnorm_kernel<op16><<<grid, 256, 0, st>>>(x, w, (op16*)out, rows, D, 1.1920928955078125e-07f);
+    if (o_dt == DT_F32) rmsnorm_kernel<float><<<grid, 256, 0, st>>>(x, w, (float*)out, rows, D, 1.1920928955078125e-07f, res);
+    else rmsnorm_kernel<op16><<<grid, 256, 0, st>>>(x, w, (op16*)out, rows, D, 1.1920928955078125e-07f, res);
+    ASRB_LAUNCH_CHECK();
+    return ASRB_OK;
+}
+
+// tgate (model.py:525-535): g [rows][ld] holds, per row, n_types blocks of D gate pre-activations followed by n_types
+// selector logits; out[r][c] = sum_i softmax(logits)_i * sigmoid(g[r][i D + c]).  One warp per row.
+__global__ void tgate_combine_kernel(const op16* __restrict__ g, int64_t ld, op16* __restrict__ out, int64_t rows, int D, int n_types) {
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31;
+    const op16* gr = g + row * ld;
+    float t[8], mx = -INFINITY, sum = 0.f;
+    for (int i = 0; i < n_types; ++i) { t[i] = io<op16>::ld(gr + (int64_t)n_types * D + i); mx = fmaxf(mx, t[i]); }
+    for (int i = 0; i < n_types; ++i) { t[i] = __expf(t[i] - mx); sum += t[i]; }
+    const float inv = 1.0f / sum;
+    for (int c = lane; c < D; c += 32) {
+        float acc = 0.f;
+        for (int i = 0; i < n_types; ++i) acc = fmaf(t[i] * inv, sigmoid_fast(io<op16>::ld(gr + (int64_t)i * D + c)), acc);
+        io<op16>::st(out + row * D + c, acc);
+    }
+}
+int launch_tgate_combine(const void* g, int64_t ld, void* out, int64_t rows, int D, int n_types, cudaStream_t st) {
+    if (n_types < 1 || n_types > 8) return fail(ASRB_E_ARG, "tgate: %d types unsupported (1..8)", n_types);
+    ProfScope ps("tgate_combine", st, 0.0, 2.0 * rows * ((double)n_types * D + D));
+    tgate_combine_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>((const op16*)g, ld, (op16*)out, rows, D, n_types);
     ASRB_LAUNCH_CHECK();
     return ASRB_OK;
 }

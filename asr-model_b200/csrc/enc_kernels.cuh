@@ -56,7 +56,10 @@ int launch_attention_tc_ex(const void* q, int ldq, int q_col0, const void* kv, i
                            int64_t B, int64_t Tq, int64_t Tk, int D, int H, float scale, cudaStream_t st);
 
 // RMSNorm rows (nn.RMSNorm, eps = fp32 machine eps): out = x / sqrt(mean(x^2)+eps) * w; out fp32 or op16 (an MMA operand)
-int launch_rmsnorm(const float* x, const float* w, void* out, DType o_dt, int64_t rows, int D, cudaStream_t st);
+int launch_rmsnorm(const float* x, const float* w, void* out, DType o_dt, int64_t rows, int D, cudaStream_t st,
+                   const float* res = nullptr);            // optional: out = res + norm(x)
+// tgate (model.py:525-535) on the gate / selector pre-activations of one GEMM: see enc_kernels.cu
+int launch_tgate_combine(const void* g, int64_t ld, void* out, int64_t rows, int D, int n_types, cudaStream_t st);
 // rotary (model.py:198-214) + per-head RMSNorm (model.py:307) in place on x [B*T][ld] (fp32 or op16), heads at h*hd
 int launch_rotary_headnorm(void* x, DType dt, int64_t ld, const float* xa, const float* ln_w, const float* freqs,
                            int64_t B, int64_t T, int D, int H, float pre_scale, cudaStream_t st);

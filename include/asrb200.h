@@ -216,6 +216,18 @@ int asrb_attention_forward_cached(asrb_attention* att, const float* x, int64_t b
                                   const void* kv_cache, int64_t kv_frames, float* out,
                                   void* workspace, size_t workspace_bytes, void* stream);
 
+/* residual.mlp applied to encoded audio (model.py:573-574, 583): shared RMSNorm -> tgate (model.py:525-535) ->
+ * Linear(D, n D) -> GELU -> Linear(n D, D) -> the same RMSNorm, on the tensor cores (dims % 128 == 0).  Keys as in a reference
+ * `residual` state_dict: ln.weight, mlp.1.ga.{i}.0.{weight,bias}, mlp.1.cs.0.{weight,bias}, mlp.2.{weight,bias},
+ * mlp.4.{weight,bias}.  x, out: [batch][frames][dims] fp32 device; add_residual != 0: out = x + mlp(x) (model.py:583). */
+typedef struct asrb_mlp asrb_mlp;
+int  asrb_mlp_create(int32_t dims, int32_t n_types, int n_tensors, const char* const* names,
+                     const float* const* host_data, const int64_t* numels, asrb_mlp** mlp);
+void asrb_mlp_destroy(asrb_mlp* mlp);
+size_t asrb_mlp_workspace_bytes(const asrb_mlp* mlp, int64_t batch, int64_t frames);
+int asrb_mlp_forward(asrb_mlp* mlp, const float* x, int64_t batch, int64_t frames, int add_residual,
+                     float* out, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------
  * Measurement aid (process-wide; off by default, not for production): between
  * asrb_profile_begin() and asrb_profile_end() every kernel launch of this library is

@@ -39,4 +39,5 @@ from .encoder import (  # noqa: F401
     encoder_state_dict_spec,
     random_encoder_state_dict,
 )
-from .attention import rotary_apply, attention_forward, random_attention_state_dict  # noqa: F401
+from .attention import (rotary_apply, attention_forward, random_attention_state_dict,  # noqa: F401
+                        residual_mlp_forward, random_mlp_state_dict)

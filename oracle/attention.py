@@ -91,3 +91,36 @@ def random_attention_state_dict(dims: int, head: int, seed: int = 0, perturb: bo
         "ln.weight": ones(hd),
         "rot.lin.weight": U((hd // 2, dims), b), "rot.lin.bias": U((hd // 2,), b),
     }
+
+
+def residual_mlp_forward(sd: SD, x: torch.Tensor) -> torch.Tensor:
+    """``residual.mlp`` (model.py:573-574): ``ln -> tgate -> Linear(D, 3 D) -> GELU -> Linear(3 D, D) -> ln`` with ONE shared
+    ``nn.RMSNorm`` (``n.ln``) at both ends and ``tgate`` (model.py:525-535) = ``sum_i softmax(cs(x))_i * sigmoid(ga_i(x))``
+    -- a gate that does not multiply its input.  ``x [B, T, D]`` -> ``[B, T, D]`` (the caller adds the residual,
+    model.py:583)."""
+    n_types = sd["mlp.1.cs.0.weight"].shape[0]
+    h = _rms_norm(x, sd["ln.weight"])
+    types = torch.softmax(F.linear(h, sd["mlp.1.cs.0.weight"], sd["mlp.1.cs.0.bias"]), dim=-1)
+    ga = torch.stack([torch.sigmoid(F.linear(h, sd[f"mlp.1.ga.{i}.0.weight"], sd[f"mlp.1.ga.{i}.0.bias"]))
+                      for i in range(n_types)], dim=-1)
+    t = torch.sum(ga * types.unsqueeze(2), dim=-1)
+    y = F.linear(F.gelu(F.linear(t, sd["mlp.2.weight"], sd["mlp.2.bias"])), sd["mlp.4.weight"], sd["mlp.4.bias"])
+    return _rms_norm(y, sd["ln.weight"])
+
+
+def random_mlp_state_dict(dims: int, num_types: int = 3, seed: int = 0) -> SD:
+    """The ``ln`` / ``mlp`` entries of a reference ``residual`` state_dict (default-init scales, perturbed norm weight)."""
+    gen = torch.Generator().manual_seed(seed)
+
+    def U(shape, bound):
+        return (torch.rand(shape, generator=gen) * 2 - 1) * bound
+
+    b = 1.0 / math.sqrt(dims)
+    sd = {"ln.weight": 1.0 + U((dims,), 0.3)}
+    for i in range(num_types):
+        sd[f"mlp.1.ga.{i}.0.weight"], sd[f"mlp.1.ga.{i}.0.bias"] = U((dims, dims), b), U((dims,), b)
+    sd["mlp.1.cs.0.weight"], sd["mlp.1.cs.0.bias"] = U((num_types, dims), b), U((num_types,), b)
+    sd["mlp.2.weight"], sd["mlp.2.bias"] = U((dims * num_types, dims), b), U((dims * num_types,), b)
+    b2 = 1.0 / math.sqrt(dims * num_types)
+    sd["mlp.4.weight"], sd["mlp.4.bias"] = U((dims, dims * num_types), b2), U((dims,), b2)
+    return sd

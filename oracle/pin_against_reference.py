@@ -175,6 +175,24 @@ def main():
     assert dx <= 2e-6, dx
     att_gold["att_xa"], att_gold["att_cross_y"] = xa.numpy(), refx.numpy()
     report["cases"]["attention_rotary_cross"] = {"oracle_vs_ref_maxabs": dx, "cfg": [D, H, T, 53]}
+    # residual.mlp (model.py:573-574): shared RMSNorm, tgate, Linear-GELU-Linear -- the reference's own sub-module, called directly
+    Dm = 128
+    res = model.residual(Dm, 4, 2, "gelu", "rmsnorm").eval()
+    msd = oracle.random_mlp_state_dict(Dm, 3, seed=5)
+    full = res.state_dict()
+    for k, v in msd.items():
+        assert tuple(full[k].shape) == tuple(v.shape), k
+        full[k] = v
+    full["mlp.0.weight"] = full["mlp.5.weight"] = msd["ln.weight"]          # the shared norm appears under three names
+    res.load_state_dict(full)
+    xm = torch.randn(2, 29, Dm, generator=g)
+    with torch.no_grad():
+        refm = res.mlp(xm)
+    oursm = oracle.residual_mlp_forward(msd, xm)
+    dm = float((refm - oursm).abs().max())
+    assert dm <= 2e-6, dm
+    att_gold["mlp_x"], att_gold["mlp_y"] = xm.numpy(), refm.numpy()
+    report["cases"]["residual_mlp"] = {"oracle_vs_ref_maxabs": dm, "cfg": [Dm, 3, 29]}
     np.savez_compressed(os.path.join(GOLD, "attention.npz"), **att_gold)
 
     with open(os.path.join(GOLD, "PINNED.json"), "w") as f:

@@ -298,3 +298,24 @@ def test_attention_block_on_tensor_cores_with_kv_reuse(ab, D, H, B, T):
         yx = a(xq.cuda(), kv=kv).cpu()
         e = (yx - refx).abs()
         assert bool((e <= 2e-2 + 1e-2 * refx.abs()).all()), (Tq, float(e.max()))
+
+
+def test_residual_mlp_on_tensor_cores(ab, golden):
+    """residual.mlp (model.py:573-574) -- against the reference's own output (fixture) and the oracle."""
+    sd = oracle.random_mlp_state_dict(128, 3, seed=5)
+    m = ab.ResidualMLP(128, 3)
+    m.load_state_dict(sd)
+    x = torch.from_numpy(golden["attention"]["mlp_x"])
+    ref = torch.from_numpy(golden["attention"]["mlp_y"])
+    y = m(x.cuda()).cpu()
+    err = (y - ref).abs()
+    print(f"residual.mlp vs reference fixture: max-abs {float(err.max()):.5f}  refmax {float(ref.abs().max()):.2f}")
+    assert bool((err <= 2e-2 + 1e-2 * ref.abs()).all())
+    sd = oracle.random_mlp_state_dict(512, 3, seed=6)
+    m = ab.ResidualMLP(512, 3)
+    m.load_state_dict(sd)
+    x = torch.randn(3, 333, 512, generator=torch.Generator().manual_seed(8))
+    ref = oracle.residual_mlp_forward(sd, x)
+    y = m(x.cuda()).cpu()
+    assert bool(((y - ref).abs() <= 2e-2 + 1e-2 * ref.abs()).all())
+    assert bool(((m(x.cuda(), add_residual=True).cpu() - (x + ref)).abs() <= 2e-2 + 1e-2 * (x + ref).abs()).all())

@@ -105,6 +105,12 @@ def test_attention_matches_reference_fixture(golden):
     assert float((yx - torch.from_numpy(golden["attention"]["att_cross_y"])).abs().max()) <= 1e-5
 
 
+def test_residual_mlp_matches_reference_fixture(golden):
+    sd = oracle.random_mlp_state_dict(128, 3, seed=5)
+    y = oracle.residual_mlp_forward(sd, torch.from_numpy(golden["attention"]["mlp_x"]))
+    assert float((y - torch.from_numpy(golden["attention"]["mlp_y"])).abs().max()) <= 1e-5
+
+
 def test_encoder_param_count():
     spec = oracle.encoder_state_dict_spec(80, 512, 4, False)
     n = sum(int(np.prod(s)) for k, s in spec.items()
