@@ -203,3 +203,29 @@ def test_frontend_writes_every_element_and_nothing_else(ab, n_mels, n_fft, n):
         assert bool((buf[:guard] == 12345.0).all()) and bool((buf[-guard:] == 12345.0).all())
     # the fused 16-bit channels-last output of the PCM -> hidden path is covered by the encoder's NaN-filled result tensor
     # (tests/test_gpu_encoder.py::test_full_size_64x30s_batch_properties)
+
+
+@pytest.mark.parametrize("n_fft,hop", [(400, 128), (400, 200), (1024, 256), (400, 50), (1024, 190)])
+def test_other_hop_lengths_take_the_generic_path(ab, n_fft, hop):
+    """`hop_length` is a free parameter of extract_features (essentials.py:423-425); 160 has a specialised kernel (compile-time
+    frame offsets, bank-skewed staging), every other value runs the run-time-hop instantiation -- incl. hops that are not a
+    multiple of 4 (no 16-byte staging) and the pooled waveform feature taken in the same pass."""
+    from asr_model_b200.frontend import LogMel
+    n = 16000 + 123
+    waves = synth.make_batch("WH2Z", n)
+    ref = oracle.log_mel_batch(waves, 80, n_fft, hop=hop)
+    fe = LogMel(80, n_fft, hop)
+    out = fe(waves.cuda()).cpu()
+    assert out.shape == ref.shape
+    assert float((out - ref).abs().max()) <= TOL
+    lengths = [n, 7000, 1234, 0]
+    refl = oracle.log_mel_batch(waves, 80, n_fft, hop=hop, lengths=lengths)
+    assert float((fe(waves.cuda(), lengths=torch.tensor(lengths)).cpu() - refl).abs().max()) <= TOL
+    if 16000 % hop == 0:
+        from asr_model_b200.frontend import pooled_target
+        tg = pooled_target(n, hop)
+        if 0 < tg < n and tg <= fe.num_frames(n):
+            mel, pooled = fe(waves.cuda(), pooled_target=tg)
+            assert torch.equal(mel.cpu(), out)
+            for b in range(4):
+                assert float((pooled[b].cpu() - oracle.waveform_feature(waves[b], hop=hop)).abs().max()) <= 1e-6
