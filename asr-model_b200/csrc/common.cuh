@@ -66,7 +66,7 @@ __device__ __forceinline__ float gelu_erf(float x) {          // nn.GELU() exact
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
 __device__ __forceinline__ float siluf_(float x) { return x * sigmoidf_(x); }
 
-// fast variants for the bf16 path (error far below one bf16 ulp)
+// fast variants for the tensor-core path (error far below one rounding of the 16-bit result)
 __device__ __forceinline__ float rcp_approx(float x) {           // MUFU.RCP, 1 ulp, no slow path
     float y;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -84,7 +84,7 @@ __device__ __forceinline__ float tanh_approx(float x) {          // MUFU.TANH, m
 }
 // erf-GELU through one MUFU: 0.5 x (1 + tanh(x q(x^2))) with q fitted so that tanh(x q) = erf(x / sqrt 2)
 // (|formula error| < 3e-5 on the whole line; q is evaluated at min(x^2, 49): tanh has long saturated there).
-// Total error incl. the MUFU bound: < 2.5e-4 |x| -- a few percent of a bf16 rounding of the result.
+// Total error incl. the MUFU bound: < 2.5e-4 |x| -- far below the 2e-2 tolerance and of the order of an fp16 rounding.
 __device__ __forceinline__ float gelu_fast(float x) {
     const float s = fminf(x * x, 49.0f);               // beyond |x| = 7 tanh has long saturated; keeps x q(s) monotone
     const float q = fmaf(fmaf(-3.58867440e-04f, s, 3.70510348e-02f), s, 7.97457818e-01f);

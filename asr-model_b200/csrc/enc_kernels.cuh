@@ -33,7 +33,7 @@ int launch_glu(const void* x, void* out, DType dt, int64_t rows, int D, cudaStre
 
 // Depthwise conv along T, channels-last: out[b,t,c] = act(sum_j w[j][c] x[b,t+j-KW/2,c] + bias[c]);
 // pos != NULL ([T][D] table from launch_pos_table) adds sinusoids(t, c) after the activation;
-// fast = approximate erf/exp (bf16 path); out may be a different storage type than x.  D % 64 == 0.
+// fast = approximate erf/exp (tensor-core path); out may be a different storage type than x.  D % 64 == 0.
 int launch_dwconv(const void* x, DType x_dt, const float* w, const float* bias, void* out, DType o_dt,
                   int64_t B, int64_t T, int D, int KW, Act act, const float* pos, bool fast, cudaStream_t st,
                   float* out32 = nullptr);     // optional fp32 copy of the output

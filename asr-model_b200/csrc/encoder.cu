@@ -43,7 +43,7 @@ struct DevPool {                      // device constants owned by a handle
     void release() { for (void* p : ptrs) cudaFree(p); ptrs.clear(); }
 };
 
-std::vector<op16> to_bf16(const std::vector<float>& v) {          // fp32 weights -> the 16-bit operand format
+std::vector<op16> to_op16_vec(const std::vector<float>& v) {          // fp32 weights -> the 16-bit operand format
     std::vector<op16> o(v.size());
     for (size_t i = 0; i < v.size(); ++i) o[i] = host_to_op16(v[i]);
     return o;
@@ -99,7 +99,7 @@ extern "C" int asrb_encoder_create(const asrb_encoder_config* cfg, int n_tensors
     if (cfg->enc) { const int hd = D / cfg->head; if (hd != 16 && hd != 32 && hd != 64 && hd != 128) return fail(ASRB_E_ARG, "asrb_encoder_create: head_dim %d unsupported", hd); }
     const bool bf = cfg->compute == ASRB_BF16;
     if (bf && (D % 128 != 0 || (cfg->enc && F % 128 != 0)))
-        return fail(ASRB_E_ARG, "asrb_encoder_create: the bf16 tensor-core variant needs dims %% 128 == 0 (got %d)", D);
+        return fail(ASRB_E_ARG, "asrb_encoder_create: the tensor-core variant needs dims %% 128 == 0 (got %d)", D);
     ASRB_TRY(require_sm100());
 
     HostTensors ht;
@@ -114,7 +114,7 @@ extern "C" int asrb_encoder_create(const asrb_encoder_config* cfg, int n_tensors
 
     {   // stems (model.py:129-135)
         GET(w1, "conv1.0.weight", (int64_t)D * M * 3); GET(b1, "conv1.0.bias", D);
-        if (bf) { auto p = to_bf16(pack_conv(w1, D, M, 3, e->CP)); UP(p, e->stem1_h); }
+        if (bf) { auto p = to_op16_vec(pack_conv(w1, D, M, 3, e->CP)); UP(p, e->stem1_h); }
         else { auto p = pack_conv(w1, D, M, 3, M); UP(p, e->stem1_f); }
         { auto v = vecf(b1, D); UP(v, e->stem1_b); }
         if (ht.has("conv2.0.weight")) {
@@ -145,7 +145,7 @@ extern "C" int asrb_encoder_create(const asrb_encoder_config* cfg, int n_tensors
             const float scale = (float)((double)g[n] / sqrt(ss));
             for (int k = 0; k < D * 3; ++k) w[(size_t)n * D * 3 + k] = vn[k] * scale;
         }
-        { auto pk = pack_conv(w.data(), D, D, 3, D); if (bf) { auto h = to_bf16(pk); UP(h, lw.wc_h); } else UP(pk, lw.wc_f); }
+        { auto pk = pack_conv(w.data(), D, D, 3, D); if (bf) { auto h = to_op16_vec(pk); UP(h, lw.wc_h); } else UP(pk, lw.wc_f); }
         { auto t = vecf(bc, D); UP(t, lw.bc); }
         GET(gm, p + "2.gamma", D); GET(bt, p + "2.beta", D);
         { auto t = vecf(gm, D); UP(t, lw.gamma); } { auto t = vecf(bt, D); UP(t, lw.beta); }
@@ -160,7 +160,7 @@ extern "C" int asrb_encoder_create(const asrb_encoder_config* cfg, int n_tensors
                     memcpy(&wi[(size_t)(tile * BN + r) * D], w1 + (size_t)src * D, sizeof(float) * D);
                     bi[tile * BN + r] = b1[src];
                 }
-            auto h = to_bf16(wi); UP(h, lw.w1_h); UP(bi, lw.b1_glu);
+            auto h = to_op16_vec(wi); UP(h, lw.w1_h); UP(bi, lw.b1_glu);
         } else { auto t = vecf(w1, (size_t)2 * D * D); UP(t, lw.w1_f); auto tb = vecf(b1, 2 * D); UP(tb, lw.b1); }
         GET(dw, p + "3.depth.weight", (int64_t)D * 15); GET(db, p + "3.depth.bias", D);
         GET(bw, p + "3.bn.weight", D); GET(bb, p + "3.bn.bias", D);
@@ -175,7 +175,7 @@ extern "C" int asrb_encoder_create(const asrb_encoder_config* cfg, int n_tensors
             UP(wf, lw.dw15); UP(bfold, lw.dw15_b);
         }
         GET(w2, p + "3.point2.weight", (int64_t)D * D); GET(b2, p + "3.point2.bias", D);
-        { auto t = vecf(w2, (size_t)D * D); if (bf) { auto h = to_bf16(t); UP(h, lw.w2_h); } else UP(t, lw.w2_f); }
+        { auto t = vecf(w2, (size_t)D * D); if (bf) { auto h = to_op16_vec(t); UP(h, lw.w2_h); } else UP(t, lw.w2_f); }
         { auto t = vecf(b2, D); UP(t, lw.b2); }
         GET(w5, p + "5.weight", (int64_t)D * 3); GET(b5, p + "5.bias", D);
         { std::vector<float> t((size_t)3 * D); for (int c = 0; c < D; ++c) for (int j = 0; j < 3; ++j) t[(size_t)j * D + c] = w5[(size_t)c * 3 + j]; UP(t, lw.dw3); }
@@ -191,7 +191,7 @@ extern "C" int asrb_encoder_create(const asrb_encoder_config* cfg, int n_tensors
         GET(g2, p + "norm2.weight", D); GET(h2, p + "norm2.bias", D);
         auto put = [&](const float* w, size_t n, float** f, op16** h) -> int {
             auto t = vecf(w, n);
-            if (bf) { auto hh = to_bf16(t); return e->pool.upload(hh, h); }
+            if (bf) { auto hh = to_op16_vec(t); return e->pool.upload(hh, h); }
             return e->pool.upload(t, f);
         };
         int r = put(wi, (size_t)3 * D * D, &e->win_f, &e->win_h);
@@ -288,7 +288,7 @@ __global__ void zero_tail_kernel(uint4* __restrict__ out, const int32_t* __restr
 }
 
 // GEMM + LayerNorm on the tensor cores: fused epilogue when the row fits TMEM (N <= 512), else
-// GEMM(+residual) to bf16 followed by the row kernel.
+// GEMM(+residual) to the 16-bit operand format followed by the row kernel.
 int tc_gemm_ln(const op16* A, const op16* W, const float* bias, const op16* res,
                const float* gamma, const float* beta, void* out, void* tmp, int64_t B, int64_t T, int K, int N,
                int taps, cudaStream_t st, const float* res32 = nullptr, float* out32 = nullptr, int out_bf16 = 0,

@@ -350,7 +350,7 @@ int tc_prepare(const TcGemmArgs& a, CUtensorMap* ma, CUtensorMap* mw, CUtensorMa
     ASRB_TRY(make_act_map(ma, a.A, a.B, a.T, a.K));
     ASRB_TRY(make_w_map(mw, a.W, a.N, a.taps * a.K, bn));
     if ((a.res32 || a.out32) && a.epilogue != TC_LN) return fail(ASRB_E_ARG, "tcgen05 GEMM: fp32 residual streams are a LayerNorm-epilogue feature");
-    if (a.out_f32 && a.epilogue == TC_LN) return fail(ASRB_E_ARG, "tcgen05 GEMM: LayerNorm epilogue stores bf16 only");
+    if (a.out_f32 && a.epilogue == TC_LN) return fail(ASRB_E_ARG, "tcgen05 GEMM: LayerNorm epilogue stores 16-bit tiles only");
     if (a.out_f32) ASRB_TRY(make_out_f32_map(mo, a.out, a.B, a.T, n_out));
     else ASRB_TRY(make_act_map(mo, a.out, a.B, a.T, n_out));
     TcParams& p = *pp;

@@ -6,7 +6,7 @@
 namespace asrb {
 
 // Per epilogue group (4 warps = 128 threads = one row each): the 16 KB staging tile of the TMA store
-// ([128][64] bf16 swizzled / [128][32] fp32 swizzled).
+// ([128][64] 16-bit swizzled / [128][32] fp32 swizzled).
 static constexpr int GROUP_SCRATCH = 16 * 1024;
 
 template <int BN> struct TcCfg {

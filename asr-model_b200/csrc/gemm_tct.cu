@@ -436,7 +436,7 @@ gemm_tct_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
 // ------------------------------------ host side -------------------------------------------
 namespace {
 
-// 2-D K-major bf16 matrix [rows][cols]: box 64 x box_rows, 128-byte swizzle
+// 2-D K-major 16-bit matrix [rows][cols]: box 64 x box_rows, 128-byte swizzle
 int make_mat_map(CUtensorMap* m, const void* base, int rows, int cols, int box_rows) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return fail(ASRB_E_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
@@ -450,7 +450,7 @@ int make_mat_map(CUtensorMap* m, const void* base, int rows, int cols, int box_r
     if (r != CUDA_SUCCESS) return fail(ASRB_E_CUDA, "cuTensorMapEncodeTiled(matrix %d x %d) -> %d", rows, cols, (int)r);
     return ASRB_OK;
 }
-// [B][T][C] bf16 activations as the B operand: dims (C, T, B), box 64 x nf x 1, OOB -> 0
+// [B][T][C] 16-bit activations as the B operand: dims (C, T, B), box 64 x nf x 1, OOB -> 0
 int make_frames_map(CUtensorMap* m, const void* base, int64_t B, int64_t T, int C, int nf) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return fail(ASRB_E_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
@@ -467,7 +467,7 @@ int make_frames_map(CUtensorMap* m, const void* base, int64_t B, int64_t T, int 
 
 }  // namespace
 
-// 128 x 128 bf16 identity: the A operand of the residual k-blocks.  One per device, created on first use
+// 128 x 128 identity (operand format): the A operand of the residual k-blocks.  One per device, created on first use
 // (asrb_encoder_create touches it, so a captured forward never allocates).
 const op16* tct_identity() {
     static std::mutex mu;

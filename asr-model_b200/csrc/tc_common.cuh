@@ -7,7 +7,7 @@
 namespace asrb {
 
 static constexpr int BM = 128;          // rows per tile = TMEM lanes
-static constexpr int BK = 64;           // bf16 per 128-byte swizzle row
+static constexpr int BK = 64;           // 16-bit elements per 128-byte swizzle row
 
 // ---------------------------------- PTX wrappers ----------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
