@@ -63,6 +63,26 @@ template <int ACT2> __device__ __forceinline__ float act2_h(float ah) {         
     return fmaf(ah, tanh_approx(ah), ah);                                        // SiLU: x sigmoid(x) = h + h tanh(h)
 }
 
+// The same on a PAIR of values (two neighbouring frames of one channel) with packed f32x2 arithmetic: identical roundings,
+// 5 packed + 2 min + 2 MUFU instructions for two GELUs instead of 14.  FFMA2 keeps the FMA pipe busy for two cycles, so the
+// pipe does the same work either way; what is saved are issue slots, which the min / MUFU / convert / store instructions
+// of these epilogues then find free.
+__device__ __forceinline__ float2 gelu_h2(float2 h) {
+    float2 s = __fmul2_rn(h, h);
+    s.x = fminf(s.x, 12.25f); s.y = fminf(s.y, 12.25f);
+    float2 q = __ffma2_rn(make_float2(-1.148375808e-02f, -1.148375808e-02f), s, make_float2(2.964082784e-01f, 2.964082784e-01f));
+    q = __ffma2_rn(q, s, make_float2(1.594915636f, 1.594915636f));
+    float2 t = __fmul2_rn(h, q);
+    t.x = tanh_approx(t.x); t.y = tanh_approx(t.y);
+    return __ffma2_rn(h, t, h);
+}
+template <int ACT2> __device__ __forceinline__ float2 act2_h2(float2 ah) {       // act2(2 ah), pairwise
+    if (ACT2 == ACT_GELU) return gelu_h2(ah);
+    if (ACT2 == ACT_GELU_GELU) return gelu_h2(__fmul2_rn(make_float2(0.5f, 0.5f), gelu_h2(ah)));
+    float2 t = make_float2(tanh_approx(ah.x), tanh_approx(ah.y));                // SiLU
+    return __ffma2_rn(ah, t, ah);
+}
+
 // TMEM loads without the trailing wait (several are batched before one tcgen05.wait::ld)
 __device__ __forceinline__ void tmem_ld32_nw(uint32_t taddr, float* v) {
     uint32_t* r = reinterpret_cast<uint32_t*>(v);
@@ -113,24 +133,33 @@ template <bool MASK, int NO, int ACT2, bool OBF>
 __device__ __forceinline__ void dw3_chunk(float (&v)[32], float& pa, float& pb, float hbias, const Dw3& k, const TctParams& p,
                                           int tS, int t_lo, int t_hi, bool skip2, bool zero_first, int64_t row0 /* b*T */, int c) {
     const int ld = NO ? NO : p.n_out;
+    const float2 half2 = make_float2(0.5f, 0.5f), hb2 = make_float2(hbias, hbias);
+    float2 g[17];                                                             // g[m + 1] = activated frames (tS + 2m, tS + 2m + 1)
+    g[0] = make_float2(pa, pb);                                               // frames tS - 2, tS - 1
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = gelu_h(fmaf(v[i], 0.5f, hbias));      // GELU(acc + bias)   (model.py:145)
+    for (int m = 0; m < 16; ++m) g[m + 1] = gelu_h2(__ffma2_rn(make_float2(v[2 * m], v[2 * m + 1]), half2, hb2));   // GELU(acc + bias)   (model.py:145)
     if (MASK) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) if (tS + i < 0 || tS + i >= p.T) v[i] = 0.f;
-    } else if (zero_first) v[0] = 0.f;                                        // frame -1: conv zero padding
+        for (int m = 0; m < 16; ++m) {
+            if (tS + 2 * m < 0 || tS + 2 * m >= p.T) g[m + 1].x = 0.f;
+            if (tS + 2 * m + 1 < 0 || tS + 2 * m + 1 >= p.T) g[m + 1].y = 0.f;
+        }
+    } else if (zero_first) g[1].x = 0.f;                                      // frame -1: conv zero padding
+    pa = g[16].x; pb = g[16].y;
     const int64_t e0 = (row0 + tS - 1) * ld + c;                              // element of output j = 0
-    const float qa = pa, qb = pb;
-    pa = v[30]; pb = v[31];
+    const float2 w0 = make_float2(k.w0, k.w0), w2 = make_float2(k.w2, k.w2), kb = make_float2(k.b, k.b);
 #pragma unroll
     for (int hf = 0; hf < 2; ++hf) {                                          // two halves of 16 outputs: bounds the live registers
         float o[16];
 #pragma unroll
-        for (int jj = 0; jj < 16; ++jj) {
-            const int j = hf * 16 + jj;
-            const float x0 = j >= 2 ? v[j >= 2 ? j - 2 : 0] : (j == 0 ? qa : qb);
-            const float x1 = j >= 1 ? v[j >= 1 ? j - 1 : 0] : qb;
-            o[jj] = act2_h<ACT2>(fmaf(k.w2, v[j], fmaf(k.w1, x1, fmaf(k.w0, x0, k.b))));
+        for (int mm = 0; mm < 8; ++mm) {                                      // outputs j = 2m, 2m + 1 (frames tS - 1 + j): taps on frames j - 2, j - 1, j of the chunk
+            const int m = hf * 8 + mm;
+            // output j uses activated chunk frames j - 2, j - 1, j; in pairs: (2m-2, 2m-1) = g[m], (2m, 2m+1) = g[m+1], the middle tap straddles both
+            float2 t = __ffma2_rn(w0, g[m], kb);
+            t.x = fmaf(k.w1, g[m].y, t.x);
+            t.y = fmaf(k.w1, g[m + 1].x, t.y);
+            t = act2_h2<ACT2>(__ffma2_rn(w2, g[m + 1], t));
+            o[2 * mm] = t.x; o[2 * mm + 1] = t.y;
         }
         const int tj = tS - 1 + hf * 16;                                      // frame of o[0]
         const int64_t eh = e0 + (int64_t)(hf * 16) * ld;
@@ -151,9 +180,13 @@ __device__ __forceinline__ void dw3_chunk(float (&v)[32], float& pa, float& pb, 
 }
 
 // ---- depthwise-15 over the 44-frame window h[] (window index i <-> frame tw + i) of one channel: emits the 28
-// outputs of frames tw + 8 .. tw + 35.  k[0..14] taps and k[15] bias, halved.  MASK: the window touches a frame
-// outside [0, T) (conv zero padding; outputs past T are dropped).  4 outputs x 2 partial sums = 8 independent
-// FFMA chains at a time. ----
+// outputs of frames tw + 8 .. tw + 35: output o = bias + sum_t k[t] h[o + 1 + t].  k[0..14] taps and k[15] bias, halved.
+// MASK: the window touches a frame outside [0, T) (conv zero padding; outputs past T are dropped).
+// Packed f32x2 arithmetic on PAIRS of neighbouring outputs.  A packed operand must be an aligned register pair
+// P_m = (h[2m], h[2m+1]); for outputs (o, o+1) tap t needs (h[o+1+t], h[o+2+t]), which is such a pair only when o + 1 + t is
+// even.  So the odd taps are summed for the output pairs (2a, 2a+1) and the even taps (and the bias) for the pairs (2b-1, 2b),
+// each with aligned operands only, and one scalar add per output joins the two: 218 FFMA2 + 28 FADD per 28 outputs instead
+// of 420 FFMA + 28 FMUL + 28 FADD -- the same work for the FMA pipe, half the issue slots. ----
 template <bool MASK, int NO, int ACT2>
 __device__ __forceinline__ void dw15_emit(float (&h)[44], const float (&k)[16], uint16_t* op, int ldr, int tw, int T) {
     const int ld = NO ? NO : ldr;
@@ -161,24 +194,28 @@ __device__ __forceinline__ void dw15_emit(float (&h)[44], const float (&k)[16], 
 #pragma unroll
         for (int i = 0; i < 44; ++i) if (tw + i < 0 || tw + i >= T) h[i] = 0.f;
     }
+    auto P = [&](int m) { return make_float2(h[2 * m], h[2 * m + 1]); };
+    float2 kk[16];
 #pragma unroll
-    for (int j0 = 0; j0 < 28; j0 += 4) {
-        float s0[4], s1[4];
+    for (int t = 0; t < 16; ++t) kk[t] = make_float2(k[t], k[t]);
+    // F_b: bias + even taps for outputs (2b - 1, 2b); computed one step ahead of the E pair that needs it
+    auto even_taps = [&](int b) {
+        float2 f = kk[15];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) { s0[q] = k[15]; s1[q] = k[14] * h[j0 + q + 15]; }
+        for (int u = 0; u < 8; ++u) f = __ffma2_rn(kk[2 * u], P(b + u), f);
+        return f;
+    };
+    float2 f_lo = even_taps(0);
 #pragma unroll
-        for (int i = 0; i < 7; ++i) {
+    for (int a = 0; a < 14; ++a) {
+        const float2 f_hi = even_taps(a + 1);
+        float2 e = __fmul2_rn(kk[1], P(a + 1));                                // odd taps for outputs (2a, 2a + 1)
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                s0[q] = fmaf(k[2 * i], h[j0 + q + 1 + 2 * i], s0[q]);
-                s1[q] = fmaf(k[2 * i + 1], h[j0 + q + 2 + 2 * i], s1[q]);
-            }
-        }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const float o = act2_h<ACT2>(s0[q] + s1[q]);
-            if (!MASK || tw + 8 + j0 + q < T) st16<false>(op + (int64_t)(j0 + q) * ld, o);
-        }
+        for (int u = 1; u < 7; ++u) e = __ffma2_rn(kk[2 * u + 1], P(a + 1 + u), e);
+        const float2 o = act2_h2<ACT2>(make_float2(e.x + f_lo.y, e.y + f_hi.x));
+        if (!MASK || tw + 8 + 2 * a < T) st16<false>(op + (int64_t)(2 * a) * ld, o.x);
+        if (!MASK || tw + 8 + 2 * a + 1 < T) st16<false>(op + (int64_t)(2 * a + 1) * ld, o.y);
+        f_lo = f_hi;
     }
 }
 
@@ -374,9 +411,14 @@ gemm_tct_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
                 mbar_wait_backoff(tfull_bar(a), aph, 32, 256);
                 tc_fence_after();
                 float h[44];
-                auto glu = [&](float v, float gate) {       // (v + bv) * sigmoid(gate + bg) = hv + hv tanh((gate + bg) / 2), hv = (v + bv) / 2
-                    const float hv = fmaf(v, 0.5f, hb0);
-                    return fmaf(hv, tanh_approx(fmaf(gate, 0.5f, hb1)), hv);
+                // (v + bv) * sigmoid(gate + bg) = hv + hv tanh((gate + bg) / 2), hv = (v + bv) / 2, on pairs of frames
+                const float2 half2 = make_float2(0.5f, 0.5f), hb0_2 = make_float2(hb0, hb0), hb1_2 = make_float2(hb1, hb1);
+                auto glu2 = [&](float& v0, float& v1, float g0, float g1) {
+                    const float2 hv = __ffma2_rn(make_float2(v0, v1), half2, hb0_2);
+                    float2 ga = __ffma2_rn(make_float2(g0, g1), half2, hb1_2);
+                    ga.x = tanh_approx(ga.x); ga.y = tanh_approx(ga.y);
+                    const float2 r = __ffma2_rn(hv, ga, hv);
+                    v0 = r.x; v1 = r.y;
                 };
                 {   // pass 0: the 44-column window of the warp's first group
                     const int ws = 28 * ((g & 1) * 2), tw = tb + ws;
@@ -386,7 +428,7 @@ gemm_tct_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
                         tmem_ld32_nw(acc + 128 + ws, gt);
                         tmem_ld_wait();
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) h[i] = glu(h[i], gt[i]);
+                        for (int i = 0; i < 32; i += 2) glu2(h[i], h[i + 1], gt[i], gt[i + 1]);
                     }
                     {
                         float gt[12];
@@ -396,7 +438,7 @@ gemm_tct_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
                         tmem_ld4_nw(acc + 128 + ws + 40, gt + 8);
                         tmem_ld_wait();
 #pragma unroll
-                        for (int i = 0; i < 12; ++i) h[32 + i] = glu(h[32 + i], gt[i]);
+                        for (int i = 0; i < 12; i += 2) glu2(h[32 + i], h[33 + i], gt[i], gt[i + 1]);
                     }
                     uint16_t* op = p.out + (row0 + tw + 8) * ld + c;
                     if (tw >= 0 && tw + 43 < p.T) dw15_emit<false, NO, ACT2>(h, k, op, ld, tw, p.T);
@@ -416,7 +458,7 @@ gemm_tct_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
                     tc_fence_before();
                     mbar_arrive(tempty_bar(a));             // this warp's last TMEM read of the unit
 #pragma unroll
-                    for (int i = 0; i < 28; ++i) h[16 + i] = glu(h[16 + i], gt[i]);
+                    for (int i = 0; i < 28; i += 2) glu2(h[16 + i], h[17 + i], gt[i], gt[i + 1]);
                     uint16_t* op = p.out + (row0 + tw + 8) * ld + c;
                     if (tw >= 0 && tw + 43 < p.T) dw15_emit<false, NO, ACT2>(h, k, op, ld, tw, p.T);
                     else dw15_emit<true, NO, ACT2>(h, k, op, ld, tw, p.T);
