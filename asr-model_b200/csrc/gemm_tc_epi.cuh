@@ -32,15 +32,26 @@ __device__ __forceinline__ float act_fast(float v, int act) {
         default: return v;
     }
 }
+// gelu_fast on a pair of values with packed f32x2 arithmetic (same roundings; half the issue slots for the multiplies and FMAs)
+__device__ __forceinline__ float2 gelu_fast2(float2 x) {
+    float2 s = __fmul2_rn(x, x);
+    s.x = fminf(s.x, 49.0f); s.y = fminf(s.y, 49.0f);
+    float2 q = __ffma2_rn(make_float2(-3.58867440e-04f, -3.58867440e-04f), s, make_float2(3.70510348e-02f, 3.70510348e-02f));
+    q = __ffma2_rn(q, s, make_float2(7.97457818e-01f, 7.97457818e-01f));
+    const float2 hx = __fmul2_rn(make_float2(0.5f, 0.5f), x);
+    float2 t = __fmul2_rn(x, q);
+    t.x = tanh_approx(t.x); t.y = tanh_approx(t.y);
+    return __ffma2_rn(hx, t, hx);
+}
 __device__ __forceinline__ void act_fast32(float (&v)[32], int act) {      // switch hoisted out of the element loop
     switch (act) {
         case ACT_GELU:
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = gelu_fast(v[i]);
+            for (int i = 0; i < 32; i += 2) { const float2 y = gelu_fast2(make_float2(v[i], v[i + 1])); v[i] = y.x; v[i + 1] = y.y; }
             break;
         case ACT_GELU_GELU:
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = gelu_fast(gelu_fast(v[i]));
+            for (int i = 0; i < 32; i += 2) { const float2 y = gelu_fast2(gelu_fast2(make_float2(v[i], v[i + 1]))); v[i] = y.x; v[i + 1] = y.y; }
             break;
         case ACT_SILU:
 #pragma unroll
