@@ -1,5 +1,5 @@
 """The tcgen05 attention kernel alone, timed in a steady loop: python tools/attn_bench.py [B] [T] [D] [H] [iters]
-(ASRB_ATTN_PAIR=0 selects the cta_group::1 multicast kernel at head_dim 128.)"""
+"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -25,4 +25,4 @@ for _ in range(iters):
 e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / iters
-print(f"attention B={B} T={T} D={D} H={H} pair={os.environ.get('ASRB_ATTN_PAIR', '1')}: {ms:.4f} ms  {4.0 * B * T * T * D / ms / 1e9:.1f} TFLOP/s")
+print(f"attention B={B} T={T} D={D} H={H}: {ms:.4f} ms  {4.0 * B * T * T * D / ms / 1e9:.1f} TFLOP/s")
