@@ -15,13 +15,15 @@
 // a CTA pair owns one 256-column half each and swaps row sums over DSMEM).  The two epilogues with a
 // fused depthwise convolution (TC_GLU_DW, TC_RES_ACT_DW) live in gemm_tct.cu (lanes = channels).
 #include "gemm_tc_epi.cuh"
+#include <cstdlib>
 
 namespace asrb {
 
 template <int BN, int EPI>
 __global__ void __launch_bounds__(TcCfg<BN>::THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
-               const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_ah, const TcParams p) {
+               const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_ah,
+               const __grid_constant__ CUtensorMap map_ak, const TcParams p) {
     using C = TcCfg<BN>;
     constexpr int STAGES = C::STAGES, NG = C::NG;
     extern __shared__ __align__(1024) unsigned char smem[];                  // SWIZZLE_128B tiles need 1024-B alignment
@@ -36,7 +38,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * STAGES + a); };
     auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * STAGES + 2 + a); };
     auto xbar = [&](int a) { return bar0 + 8u * (2 * STAGES + 4 + a); };
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 6);
+    auto a_full = [&](int i) { return bar0 + 8u * (2 * STAGES + 6 + i); };   // k3one: the 130-row frame tile of a k-block
+    auto a_empty = [&](int i) { return bar0 + 8u * (2 * STAGES + 8 + i); };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 10);
+    // k3one layout of the operand area: [2 frame tiles of 130 rows x 128 B, 17 KB apart][STAGES weight tiles of B_BYTES]
+    constexpr int A1_STRIDE = 17 * 1024, A1_BYTES = 130 * 128;
+    static_assert(2 * A1_STRIDE + STAGES * C::B_BYTES <= STAGES * C::STAGE_BYTES, "k3one operand area");
 
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // provably warp-uniform role index
     constexpr bool is_ln = EPI == TC_LN;
@@ -49,17 +56,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int kb_per_tap = p.K / BK;
     const int num_kb = p.taps * kb_per_tap;
     const int pad = p.taps / 2;
+    const bool k3one = p.k3one != 0 && p.taps == 3 && nbu == 1;              // one accumulator chunk per unit: frame tile fetched once per k-block
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_out) : "memory");
         if (is_ln) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_ah) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_ak) : "memory");
     }
     if (warp == 1 && lane == 0) {
         // pair (cl = 2): both CTAs read the same frame tile, so each loads half of it and multicasts it to both; a
         // slot is free once BOTH CTAs' MMAs have consumed it (two arrivals on empty)
-        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), (uint32_t)cl); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), k3one ? 1u : (uint32_t)cl); }
+        for (int i = 0; i < 2; ++i) { mbar_init(a_full(i), 1); mbar_init(a_empty(i), (uint32_t)cl); }
         for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), NG * 128); mbar_init(xbar(a), BM); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -78,11 +88,39 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         // one elected lane issues.
         const bool leader = elect_one();
         int s = 0; uint32_t ph = 0;
+        int ab = 0; uint32_t aph = 0;                                         // k3one: frame-tile ring
         for (int u = u_first; u < units; u += u_step) {
             const int m = is_ln ? u : u / p.n_chunks;
             const int nb0 = is_ln ? (int)crank : u % p.n_chunks;
             const int b = m / p.tiles_per_utt, t0 = (m % p.tiles_per_utt) * p.rows_out - p.halo;
             if (tile_is_padding(p.frames_eff, b, t0)) continue;               // ragged batch: nothing of this tile is needed
+            if (k3one) {
+                // one 130-row frame tile per k-block (rows t0 - 1 .. t0 + 128; in a pair CTA 0 fetches rows 0..63, CTA 1 rows
+                // 64..129, both multicast), then the three taps' weight tiles
+                const int n0 = nb0 * BN;
+                for (int kc = 0; kc < kb_per_tap; ++kc) {
+                    mbar_wait_sleep(a_empty(ab), aph ^ 1, 32);
+                    if (leader) {
+                        mbar_expect_tx(a_full(ab), A1_BYTES);
+                        const uint32_t aa = smem_u32(smem + ab * A1_STRIDE);
+                        if (cl == 1) tma_load_3d(aa, &map_ak, kc * BK, t0 - 1, b, a_full(ab));                     // 130-row box
+                        else if (crank == 0) tma_load_3d_mc(aa, &map_ah, kc * BK, t0 - 1, b, a_full(ab), (uint16_t)3);
+                        else tma_load_3d_mc(aa + 64 * 128, &map_ak, kc * BK, t0 - 1 + 64, b, a_full(ab), (uint16_t)3);   // 66-row box
+                    }
+                    __syncwarp();
+                    if (++ab == 2) { ab = 0; aph ^= 1; }
+                    for (int tap = 0; tap < 3; ++tap) {
+                        mbar_wait_sleep(empty_bar(s), ph ^ 1, 32);
+                        if (leader) {
+                            mbar_expect_tx(full_bar(s), C::B_BYTES);
+                            tma_load_2d(smem_u32(smem + 2 * A1_STRIDE + s * C::B_BYTES), &map_w, (tap * kb_per_tap + kc) * BK, n0, full_bar(s));
+                        }
+                        __syncwarp();
+                        if (++s == STAGES) { s = 0; ph ^= 1; }
+                    }
+                }
+                continue;
+            }
             for (int j = 0; j < nbu; ++j) {
                 const int n0 = (nb0 + j) * BN;
                 for (int kb = 0; kb < num_kb; ++kb) {
@@ -108,6 +146,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const bool leader = elect_one();
         constexpr uint32_t idesc = make_idesc(BN);
         int s = 0; uint32_t ph = 0; int it = 0;
+        int ab = 0; uint32_t abph = 0;                                        // k3one: frame-tile ring
         for (int u = u_first; u < units; u += u_step) {
             if (p.frames_eff) {
                 const int m = is_ln ? u : u / p.n_chunks;
@@ -118,6 +157,38 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             ++it;
             mbar_wait_sleep(tempty_bar(a), aph ^ 1, 32);
             tc_fence_after();
+            if (k3one) {
+                // tap `tap` of a k-block reads the frame tile from row `tap` on: the descriptor simply starts 128 B x tap into the
+                // tile.  The 128-byte swizzle is a function of the shared-memory ADDRESS (bits 4-6 ^= bits 7-9), for the TMA
+                // write and for the MMA read alike, so a start that is not 1024-byte aligned needs nothing else (measured: with
+                // the descriptor's base-offset field set to the row phase the results are wrong, with 0 they are exact)
+                const uint32_t d_tmem = tmem_base + (uint32_t)(a * BN);
+                for (int kc = 0; kc < kb_per_tap; ++kc) {
+                    mbar_wait(a_full(ab), abph);
+                    tc_fence_after();
+                    for (int tap = 0; tap < 3; ++tap) {
+                        mbar_wait(full_bar(s), ph);
+                        tc_fence_after();
+                        if (leader) {
+                            const uint32_t aa = smem_u32(smem + ab * A1_STRIDE) + (uint32_t)(tap * 128);
+                            const uint64_t adesc = make_smem_desc(aa);
+                            const uint64_t bdesc = make_smem_desc(smem_u32(smem + 2 * A1_STRIDE + s * C::B_BYTES));
+#pragma unroll
+                            for (int kk = 0; kk < BK / 16; ++kk)
+                                tc_mma(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, (uint32_t)((kc | tap | kk) != 0));
+                            tc_commit(empty_bar(s));                          // weight slots are this CTA's own
+                        }
+                        __syncwarp();
+                        if (++s == STAGES) { s = 0; ph ^= 1; }
+                    }
+                    if (leader) { if (cl > 1) tc_commit_mc(a_empty(ab), (uint16_t)3); else tc_commit(a_empty(ab)); }   // pair: the peer writes part of my frame tile
+                    __syncwarp();
+                    if (++ab == 2) { ab = 0; abph ^= 1; }
+                }
+                if (leader) tc_commit(tfull_bar(a));
+                __syncwarp();
+                continue;
+            }
             for (int j = 0; j < nbu; ++j) {
                 const uint32_t d_tmem = tmem_base + (uint32_t)((a * nbu + j) * BN);
                 for (int kb = 0; kb < num_kb; ++kb) {
@@ -320,7 +391,7 @@ bool tc_gemm_supported(int K, int N, int epi) {
 
 template <int BN, int EPI>
 static int launch_one(const CUtensorMap& ma, const CUtensorMap& mw, const CUtensorMap& mo, const CUtensorMap& mah,
-                      const TcParams& p, int units, cudaStream_t st) {
+                      const CUtensorMap& mak, const TcParams& p, int units, cudaStream_t st) {
     auto kern = gemm_tc_kernel<BN, EPI>;
     ASRB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::SMEM));
     const int cl = p.cluster;
@@ -333,7 +404,7 @@ static int launch_one(const CUtensorMap& ma, const CUtensorMap& mw, const CUtens
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = (unsigned)cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    ASRB_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mw, mo, mah, p));
+    ASRB_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mw, mo, mah, mak, p));
     ASRB_LAUNCH_CHECK();
     return ASRB_OK;
 }
@@ -360,7 +431,7 @@ int tc_prepare(const TcGemmArgs& a, CUtensorMap* ma, CUtensorMap* mw, CUtensorMa
     p.tiles_per_utt = (int)((a.T + rows_out - 1) / rows_out);
     p.m_tiles = (int)(a.B * p.tiles_per_utt);
     p.n_chunks = a.N / bn; p.n_out = n_out; p.eps = a.eps; p.out_f32 = a.out_f32; p.out_bf16 = a.out_bf16;
-    p.frames_eff = a.frames_eff;
+    p.frames_eff = a.frames_eff; p.k3one = 0;
     p.cluster = (a.epilogue == TC_LN && bn == 256 && a.N == 512) ? 2 : 1;     // the 128 x 512 row block fills TMEM: split it over a CTA pair
     *bn_out = bn;
     return ASRB_OK;
@@ -385,8 +456,11 @@ int launch_gemm_tc(const TcGemmArgs& a, cudaStream_t st) {
     ProfScope ps(tags[a.epilogue], st, 2.0 * a.B * a.T * (double)a.N * a.K * a.taps,
                  2.0 * a.B * a.T * ((double)a.K + n_out * (a.out_f32 ? 2 : 1) + (a.res ? n_out : 0)) + 2.0 * a.N * a.K * a.taps);
     CUtensorMap mah = ma;                                                    // 64-row boxes of the same tensor (pair multicast)
+    CUtensorMap mak = ma;                                                    // k3one: the 130-row frame tile (pair: its rows 64..129, 66-row boxes)
     if (p.cluster > 1) ASRB_TRY(make_act_map(&mah, a.A, a.B, a.T, a.K, BM / 2));
-#define ASRB_TC(BN_, EPI_) return launch_one<BN_, EPI_>(ma, mw, mo, mah, p, units, st)
+    if (a.taps == 3) ASRB_TRY(make_act_map(&mak, a.A, a.B, a.T, a.K, p.cluster > 1 ? 66 : 130));
+    { static int k3 = -1; if (k3 < 0) { const char* e = getenv("ASRB_K3ONE"); k3 = (e && e[0] == '0') ? 0 : 1; } p.k3one = k3; }   // ASRB_K3ONE=0: one load per tap (A/B)
+#define ASRB_TC(BN_, EPI_) return launch_one<BN_, EPI_>(ma, mw, mo, mah, mak, p, units, st)
     if (bn == 256) {
         switch (a.epilogue) {
             case TC_BIAS_ACT: ASRB_TC(256, TC_BIAS_ACT);

@@ -18,7 +18,7 @@ template <int BN> struct TcCfg {
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int XCH_BYTES = NG * BM * 8 + 2 * BM * 8;         // LN partial sums per row and group + 2 peer slots (cluster LN)
     static constexpr int SMEM = STAGES * STAGE_BYTES + NG * GROUP_SCRATCH + XCH_BYTES + 256 /*barriers + tmem slot*/;
-    static_assert((2 * STAGES + 6) * 8 + 4 <= 256, "barrier region");
+    static_assert((2 * STAGES + 10) * 8 + 4 <= 256, "barrier region");
     static_assert(SMEM <= 227 * 1024, "shared memory budget");
 };
 
@@ -72,6 +72,7 @@ struct TcParams {
     float eps;
     int halo, rows_out;          // rows_out = 128 frames per tile, halo = 0 (kept for the tile arithmetic)
     const int32_t* frames_eff;   // ragged batches: [B] frames per utterance that anything downstream still needs, or NULL
+    int k3one;                   // 3 taps: the frame tile of a k-block is fetched ONCE (130 rows) and the taps read it at row offsets
 };
 
 // Ragged batches: a tile whose first produced frame lies at or past the utterance's effective extent
