@@ -132,7 +132,6 @@ logmel_kernel(const LogmelParams p, int tiles_per_utt, int total_tiles) {
     float2* s_tw  = reinterpret_cast<float2*>(s_win + NFFT);                    // [R*R]
     float*  s_melw = reinterpret_cast<float*>(s_tw + R * R);                    // [M][kmax]
     int2*   s_meta = reinterpret_cast<int2*>(s_melw + p.M * p.kmax);            // [M]: (first bin * row pitch, taps / 4 rounded up)
-    __shared__ float s_red[64];
     __shared__ __align__(8) uint64_t s_bar;                                     // completion of the TMA-fetched PCM span
 
     const int tid = threadIdx.x;
@@ -146,9 +145,11 @@ logmel_kernel(const LogmelParams p, int tiles_per_utt, int total_tiles) {
     // A tile whose whole span lies inside the utterance (all but the first and the last two of an utterance) is fetched by
     // ONE thread with TMA bulk copies (one per frame quad when the bank skew is on) that complete on an mbarrier; the edge
     // tiles, which need zero fill, go through cp.async.
-    auto tile_geom = [&](int tile, int& b, int& t0, int64_t& s0, int& lo, int& hi) {
-        b = tile / tiles_per_utt; t0 = (tile - b * tiles_per_utt) * FB;
-        const int64_t len = clamp_len(p.lengths, b, p.n_samples);
+    // Tile geometry without divisions: a block walks the tile list in steps of gridDim.x, so (utterance, tile in utterance)
+    // advance by a constant pair with one carry, and every "frame t is a frame of the utterance" test is t * hop <= len
+    // (t < 1 + len / hop).  The length of an utterance is read once per tile, when its PCM span is requested.
+    const int step_b = (int)gridDim.x / tiles_per_utt, step_t = (int)gridDim.x - step_b * tiles_per_utt;
+    auto span_geom = [&](int t0, int64_t len, int64_t& s0, int& lo, int& hi) {
         s0 = (int64_t)t0 * hop - NFFT / 2;
         lo = s0 < 0 ? (int)(-s0) : 0;                                              // first span index that is a real sample
         const int64_t rem = len - s0;
@@ -156,11 +157,12 @@ logmel_kernel(const LogmelParams p, int tiles_per_utt, int total_tiles) {
     };
     const uint32_t pcm_bar = (uint32_t)__cvta_generic_to_shared(&s_bar);
     const uint32_t d0 = (uint32_t)__cvta_generic_to_shared(s_pcm);
-    auto prefetch = [&](int tile) -> bool {                                        // returns: fetched by TMA (wait on the mbarrier)
-        int b, t0, lo, hi; int64_t s0;
-        tile_geom(tile, b, t0, s0, lo, hi);
+    auto prefetch = [&](int b, int ti, int64_t len) -> bool {                      // returns: fetched by TMA (wait on the mbarrier)
+        const int t0 = ti * FB;
+        if (len < (int64_t)t0 * hop) { cp_async_commit(); return false; }          // a padding tile (t0 >= 1 + len / hop) reads no PCM
+        int lo, hi; int64_t s0;
+        span_geom(t0, len, s0, lo, hi);
         const float* src = p.pcm + (int64_t)b * p.stride + s0;                     // span index 0 (never dereferenced outside [lo, hi))
-        if (t0 >= 1 + (int)(clamp_len(p.lengths, b, p.n_samples) / hop)) { cp_async_commit(); return false; }   // a padding tile reads no PCM
         if (vec_ok && lo == 0 && hi == span4) {
             if (tid == 0) {
                 mbar_expect_tx(pcm_bar, (uint32_t)span4 * 4u);
@@ -194,7 +196,9 @@ logmel_kernel(const LogmelParams p, int tiles_per_utt, int total_tiles) {
     if (tid == 0) { mbar_init(pcm_bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
     __syncthreads();
     bool by_tma = false; uint32_t tma_phase = 0;
-    if (tile < total_tiles) by_tma = prefetch(tile);
+    int nb = tile / tiles_per_utt, nti = tile - nb * tiles_per_utt;                // the one division of the block
+    int64_t nlen = 0;                                                              // (nb, nti, nlen): the tile whose PCM is in flight
+    if (tile < total_tiles) { nlen = clamp_len(p.lengths, nb, p.n_samples); by_tma = prefetch(nb, nti, nlen); }
     // ---- constants, once per block ----
     for (int i = tid; i < NFFT; i += C::THREADS) s_win[i] = p.window[i];
     for (int i = tid; i < R * R; i += C::THREADS) s_tw[i] = p.twiddle[i];
@@ -212,14 +216,20 @@ logmel_kernel(const LogmelParams p, int tiles_per_utt, int total_tiles) {
         if (by_tma) { mbar_wait(pcm_bar, tma_phase); tma_phase ^= 1u; } else cp_async_wait<0>();
         __syncthreads();                                     // this tile's PCM (and the constants) are visible; the previous tile's readers are done
 
-        const int b = tile / tiles_per_utt, t0 = (tile - b * tiles_per_utt) * FB;
-        const int64_t len = clamp_len(p.lengths, b, p.n_samples);
-        const int Tb = 1 + (int)(len / hop);                 // valid frames of this utterance (<= T: len <= n_samples)
+        const int b = nb, t0 = nti * FB;                     // this tile
+        const int64_t len = nlen;
+        auto request_next = [&]() {                          // (nb, nti, nlen) move on to the tile the block takes next; its PCM is requested
+            nti += step_t; nb += step_b;
+            if (nti >= tiles_per_utt) { nti -= tiles_per_utt; ++nb; }
+            const bool has_next = tile + (int)gridDim.x < total_tiles;
+            nlen = has_next ? clamp_len(p.lengths, nb, p.n_samples) : 0;
+            if (has_next) by_tma = prefetch(nb, nti, nlen);
+        };
 
-        if (t0 >= Tb) {
-            // ---- a tile wholly past the utterance (ragged batch): DataCollator's 0.0 padding, no transform ----
+        if (len < (int64_t)t0 * hop) {
+            // ---- a tile wholly past the utterance (t0 >= 1 + len / hop, ragged batch): DataCollator's 0.0 padding, no transform ----
             __syncthreads();
-            { const int next = tile + gridDim.x; if (next < total_tiles) by_tma = prefetch(next); }
+            request_next();
             const int nf = min(FB, p.T - t0);
             if (p.out_cl) {
                 uint32_t* dst = reinterpret_cast<uint32_t*>(p.out_cl + ((int64_t)b * p.T + t0) * p.CP);
@@ -275,10 +285,15 @@ logmel_kernel(const LogmelParams p, int tiles_per_utt, int total_tiles) {
             __syncthreads();                                 // the PCM span is in registers everywhere: the transpose may overwrite it
             SmallDFT<R>::run(x);
             yq[j] = pack4(x[0]);
+            // twiddles are fetched five at a time AHEAD of the stores they feed: the compiler cannot move a shared-memory load
+            // above a store that might alias it, and one load per store leaves every load's latency exposed
 #pragma unroll
-            for (int k1 = 1; k1 < R; ++k1) {
-                const float2 tw = s_tw[k1 * R + j];
-                yq[k1 * C::YP + j] = pack4(cmul_cs(x[k1], tw.x, tw.y));
+            for (int k0 = 1; k0 < R; k0 += 5) {
+                float2 tw[5];
+#pragma unroll
+                for (int i = 0; i < 5; ++i) if (k0 + i < R) tw[i] = s_tw[(k0 + i) * R + j];
+#pragma unroll
+                for (int i = 0; i < 5; ++i) if (k0 + i < R) yq[(k0 + i) * C::YP + j] = pack4(cmul_cs(x[k0 + i], tw[i].x, tw[i].y));
             }
         }
         __syncthreads();
@@ -302,9 +317,12 @@ logmel_kernel(const LogmelParams p, int tiles_per_utt, int total_tiles) {
         {
             const float4* ep = s_e + q * (R * C::EP) + (j ? R - j : 0) * C::EP + (j == 0 ? 1 : 0);
             float* pk = s_p + j * C::PP + 4 * q;
+            cx2 zp[R / 2];                                   // all partners first (the upper half of z is dead: registers are free),
+#pragma unroll                                               // then arithmetic and stores -- loads cannot pass the power-row stores
+            for (int k2 = 0; k2 < R / 2; ++k2) zp[k2] = unpack4(ep[R / 2 - 1 - k2]);
 #pragma unroll
             for (int k2 = 0; k2 < R / 2; ++k2) {
-                const cx2 z2 = unpack4(ep[R / 2 - 1 - k2]);
+                const cx2 z2 = zp[k2];
                 const V2 ar = vadd(z[k2].re, z2.re), ai = vsub(z[k2].im, z2.im);       // 2 Re A, 2 Im A
                 const V2 br = vadd(z[k2].im, z2.im), bi = vsub(z2.re, z[k2].re);       // 2 Re B, 2 Im B
                 const V2 pa = vfma2(ar, ar, vmul2(ai, ai)), pb = vfma2(br, br, vmul2(bi, bi));
@@ -319,7 +337,7 @@ logmel_kernel(const LogmelParams p, int tiles_per_utt, int total_tiles) {
         __syncthreads();
 
         // area A is dead until the next tile's transpose: the next PCM span streams into it under the mel stage
-        { const int next = tile + gridDim.x; if (next < total_tiles) by_tma = prefetch(next); }
+        request_next();
 
         // ---- banded mel projection + log10 + (x+4)/4.  Work item = (filter m, frame quad): a thread keeps its quad and walks
         // the filters R apart; the 8 (4) lanes that share m read one power row per tap, conflict free, and the weights arrive
@@ -330,13 +348,18 @@ logmel_kernel(const LogmelParams p, int tiles_per_utt, int total_tiles) {
         {
             const int qq = tid & (C::QUADS - 1);
             const int tq = t0 + 4 * qq;                      // first frame of this thread's quad
-            const bool full = t0 + FB <= Tb;                 // every frame of the tile is a frame of the utterance (Tb <= T)
+            const bool full = (int64_t)(t0 + FB - 1) * hop <= len;   // every frame of the tile is a frame of the utterance (t0 + FB <= Tb <= T)
             const int M = p.M, kmax4 = p.kmax >> 2, T = p.T;
             const float* pq = s_p + 4 * qq;
             const float4* wbase = reinterpret_cast<const float4*>(s_melw);
             float* obase = p.out ? p.out + (int64_t)b * M * T + tq : nullptr;
             op16* cbase = s_cl + (4 * qq) * clp;
-            for (int m = tid / C::QUADS; m < M; m += R) {
+            // a thread's filters are R apart, walking its group index up and down in turns (g, 2R-1-g, 2R+g, ...): filter
+            // bands widen with m, and this way every warp gets the same share of taps before the barrier
+            const int g = tid / C::QUADS;
+            for (int mb = 0, odd = 0; mb < M; mb += R, odd ^= 1) {
+                const int m = mb + (odd ? R - 1 - g : g);
+                if (m >= M) continue;
                 const int2 meta = s_meta[m];
                 int n4 = meta.y;
                 const float4* w4 = wbase + m * kmax4;
@@ -363,6 +386,7 @@ logmel_kernel(const LogmelParams p, int tiles_per_utt, int total_tiles) {
                         for (int i = 0; i < 4; ++i) o[i] = norm(lg[i]);
                     }
                 } else {
+                    const int Tb = 1 + (int)(len / hop);     // valid frames of this utterance (<= T: len <= n_samples); last tile only
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const int t = tq + i;
@@ -376,11 +400,20 @@ logmel_kernel(const LogmelParams p, int tiles_per_utt, int total_tiles) {
                 }
             }
         }
+        // each warp publishes its own max / min (the utterance's max only when it raises what is there: a stale read can
+        // cost an atomic, never lose one): no block-wide reduction, and without the staging tile no barrier either --
+        // the next tile's first barrier orders the reuse of the power rows
         vmax = warp_max(vmax);
         vmin = -warp_max(-vmin);
-        if (lane == 0) { s_red[warp] = vmax; s_red[32 + warp] = vmin; }
-        __syncthreads();                                    // staging tile complete; P is free for the next tile
+        if (lane == 0) {                                    // back to log10: monotone, so the max of the products is the product of the max
+            if (vmax > -INFINITY) {
+                const uint32_t key = f2key(vmax * 0.30102999566398120f);
+                if (*reinterpret_cast<volatile const uint32_t*>(p.keys + b) < key) atomicMax(p.keys + b, key);
+            }
+            atomicMin(p.tile_min + tile, f2key(vmin));      // lg2 domain; +inf from a warp without valid frames: never below a floor
+        }
         if (p.out_cl) {                                     // rows of CP 16-bit values leave as 8-byte words: at CP = 128 a warp moves one frame per load / store pair
+            __syncthreads();                                // staging tile complete
             const int dpr = p.CP >> 2, M = p.M;             // 8-byte words per row
             const int nrows = min(FB, p.T - t0);
             uint2* dst = reinterpret_cast<uint2*>(p.out_cl + ((int64_t)b * p.T + t0) * p.CP);
@@ -397,16 +430,6 @@ logmel_kernel(const LogmelParams p, int tiles_per_utt, int total_tiles) {
                     const uint2 v = src[fr * spitch + ws];
                     dst[(int64_t)fr * dpr + w] = make_uint2(v.x & k0, v.y & k1);
                 }
-            }
-        }
-        if (warp == 0) {
-            float v = lane < nwarp ? s_red[lane] : -INFINITY;
-            float u = lane < nwarp ? s_red[32 + lane] : INFINITY;
-            v = warp_max(v);
-            u = -warp_max(-u);
-            if (lane == 0) {                                // back to log10: monotone, so the max of the products is the product of the max
-                if (v > -INFINITY) atomicMax(p.keys + b, f2key(v * 0.30102999566398120f));
-                p.tile_min[tile] = f2key(u);                 // lg2 domain; +inf for a tile without valid frames: never below a floor
             }
         }
     }
@@ -586,7 +609,11 @@ int logmel_pass1(const asrb_logmel_plan* pl, const float* pcm, int64_t batch, in
     p.window = pl->d_window; p.twiddle = pl->d_twiddle; p.mel_lo = pl->d_lo; p.mel_cnt = pl->d_cnt;
     p.mel_w = pl->d_w; p.out = out; p.keys = keys; p.tile_min = keys + batch;
     p.pool_out = pool_target > 0 ? pool_out : nullptr; p.pool_target = pool_target;
-    ASRB_CUDA(cudaMemsetAsync(keys, 0, sizeof(uint32_t) * batch, st));
+    ASRB_CUDA(cudaMemsetAsync(keys, 0, sizeof(uint32_t) * batch, st));                       // maxima: below every key
+    {                                                                                        // tile minima: above every key (atomicMin)
+        const int FB = logmel_tile_frames(pl);
+        ASRB_CUDA(cudaMemsetAsync(keys + batch, 0xff, sizeof(uint32_t) * (size_t)batch * (size_t)((p.T + FB - 1) / FB), st));
+    }
     const double frames = (double)batch * p.T;
     ProfScope ps("logmel_stft_mel", st, frames * 2.5 * pl->n_fft * log2((double)pl->n_fft),
                  4.0 * batch * ((double)n_samples + (double)pl->n_mels * p.T));
