@@ -99,6 +99,29 @@ def test_full_size_30s_clips(ab):
     assert float(inner) <= 2e-4
 
 
+@pytest.mark.parametrize("n_fft", [400, 1024])
+def test_blocks_walk_several_tiles_across_ragged_utterances(ab, n_fft):
+    """More frame tiles than resident blocks (12 x 30 s = 1128 / 2256 tiles), so every block walks several tiles
+    and crosses utterance boundaries with its division-free (utterance, tile) counter; lengths ragged, one empty,
+    one full.  Utterances are checked against the oracle one by one (own max, 0.0 padding) and against the same
+    utterance computed alone (bit-equal)."""
+    N = 480000
+    kinds = "WHTWHTWHTWHT"
+    waves = synth.make_batch(kinds, N)
+    lengths = [N, 0, 123457, 479999, 160, 31, 300000, 480000 - 160, 1, 200000, 399, 77777]
+    dev = waves.cuda()
+    out = ab.log_mel(dev, 80, n_fft, lengths=torch.tensor(lengths))
+    assert out.shape == (12, 80, 3001)
+    for b in (0, 2, 3, 6, 11):
+        ref = oracle.log_mel_batch(waves[b:b + 1], 80, n_fft, lengths=[lengths[b]])
+        assert float((out[b:b + 1].cpu() - ref).abs().max()) <= TOL, b
+    for b in range(12):
+        tb = 1 + lengths[b] // 160
+        assert torch.all(out[b, :, tb:] == 0.0), b
+        alone = ab.log_mel(dev[b:b + 1], 80, n_fft, lengths=torch.tensor(lengths[b:b + 1]))
+        assert torch.equal(alone[0], out[b]), b
+
+
 def test_extract_features_drop_in(ab):
     class Tok:
         def encode(self, s):
