@@ -356,10 +356,8 @@ logmel_kernel(const LogmelParams p, int tiles_per_utt, int total_tiles) {
             op16* cbase = s_cl + (4 * qq) * clp;
             // a thread's filters are R apart, walking its group index up and down in turns (g, 2R-1-g, 2R+g, ...): filter
             // bands widen with m, and this way every warp gets the same share of taps before the barrier
-            const int g = tid / C::QUADS;
-            for (int mb = 0, odd = 0; mb < M; mb += R, odd ^= 1) {
-                const int m = mb + (odd ? R - 1 - g : g);
-                if (m >= M) continue;
+            // (the sequence g, 2R-1-g, 2R+g, 4R-1-g, ... is increasing: two running indices, no select, ends at the first m >= M)
+            for (int m = tid / C::QUADS, m_next = 2 * R - 1 - m; m < M; ) {
                 const int2 meta = s_meta[m];
                 int n4 = meta.y;
                 const float4* w4 = wbase + m * kmax4;
@@ -386,30 +384,27 @@ logmel_kernel(const LogmelParams p, int tiles_per_utt, int total_tiles) {
                         for (int i = 0; i < 4; ++i) o[i] = norm(lg[i]);
                     }
                 } else {
-                    const int Tb = 1 + (int)(len / hop);     // valid frames of this utterance (<= T: len <= n_samples); last tile only
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const int t = tq + i;
                         if (t < T) {
-                            float sv = 0.f;                                     // DataCollator pad value
-                            if (t < Tb) { vmax = fmaxf(vmax, lg[i]); vmin = fminf(vmin, lg[i]); sv = norm(lg[i]); }
+                            float sv = 0.f;                                     // DataCollator pad value; t * hop <= len: t < 1 + len / hop, a frame of the utterance
+                            if ((int64_t)t * hop <= len) { vmax = fmaxf(vmax, lg[i]); vmin = fminf(vmin, lg[i]); sv = norm(lg[i]); }
                             if (!obase) cbase[i * clp + m] = to_op16(sv);
                             else obase[(int64_t)m * T + i] = sv;
                         }
                     }
                 }
+                { const int t = m + 2 * R; m = m_next; m_next = t; }
             }
         }
-        // each warp publishes its own max / min (the utterance's max only when it raises what is there: a stale read can
-        // cost an atomic, never lose one): no block-wide reduction, and without the staging tile no barrier either --
-        // the next tile's first barrier orders the reuse of the power rows
+        // each warp publishes its own max / min with fire-and-forget reductions (nothing waits for them): no block-wide
+        // reduction, and without the staging tile no barrier either -- the next tile's first barrier orders the reuse of
+        // the power rows
         vmax = warp_max(vmax);
         vmin = -warp_max(-vmin);
         if (lane == 0) {                                    // back to log10: monotone, so the max of the products is the product of the max
-            if (vmax > -INFINITY) {
-                const uint32_t key = f2key(vmax * 0.30102999566398120f);
-                if (*reinterpret_cast<volatile const uint32_t*>(p.keys + b) < key) atomicMax(p.keys + b, key);
-            }
+            if (vmax > -INFINITY) atomicMax(p.keys + b, f2key(vmax * 0.30102999566398120f));
             atomicMin(p.tile_min + tile, f2key(vmin));      // lg2 domain; +inf from a warp without valid frames: never below a floor
         }
         if (p.out_cl) {                                     // rows of CP 16-bit values leave as 8-byte words: at CP = 128 a warp moves one frame per load / store pair
