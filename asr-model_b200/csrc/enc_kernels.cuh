@@ -69,13 +69,17 @@ enum TcEpilogue { TC_BIAS_ACT = 0, TC_GLU = 1, TC_RES_ACT = 2, TC_LN = 3,
                   TC_GLU_DW = 4,        // GLU -> depthwise conv down the frames (+folded BN) -> act2
                   TC_RES_ACT_DW = 5 };  // bias + residual + act -> depthwise conv -> act2 (+ sinusoids)
 
+// The fp32 residual streams (res32 / out32) are workspace tensors in a blocked layout, [row / 32][column / 4][row % 32][4]
+// (res32_index, gemm_tc_epi.cuh): allocate res32_rows(B * T) rows.
+inline int64_t res32_rows(int64_t rows) { return (rows + 31) & ~(int64_t)31; }
+
 struct TcGemmArgs {
     const op16* A;               // [B][T][K] channels-last
     const op16* W;               // [N][taps*K] tap-major (GLU: value/gate interleaved per tile)
     const float* bias;           // [N]
     const op16* res;             // [B][T][Nout] or NULL
-    const float* res32;          // TC_LN: fp32 residual instead of res (post-norm residual streams stay fp32)
-    float* out32;                // TC_LN: optional fp32 copy of the output
+    const float* res32;          // TC_LN: fp32 residual instead of res (post-norm residual streams stay fp32); BLOCKED layout, see res32_rows
+    float* out32;                // TC_LN / TC_RES_ACT_DW: optional fp32 copy of the output, BLOCKED layout
     const float* gamma;          // TC_LN
     const float* beta;           // TC_LN
     void* out;                   // [B][T][Nout] op16 (bf16 when out_bf16: the encoder's result; fp32 when out_f32)

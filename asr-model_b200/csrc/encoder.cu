@@ -232,7 +232,7 @@ size_t enc_ws_bytes(const asrb_encoder* e, int64_t B, int64_t T) {
     auto add = [&](size_t bytes) { n = align_up(n, 256) + bytes; };
     add(rows * (e->cfg.compute == ASRB_BF16 ? e->CP : e->cfg.mels) * es);   // a0
     add(rows * D * es); add(rows * D * es);                                 // X Y
-    add(rows * D * 4); add(rows * D * es); add(rows * D * 4);               // G (fp32) U H (fp32): G, H feed depthwise convs
+    add(res32_rows(rows) * D * 4); add(rows * D * es); add(res32_rows(rows) * D * 4);   // G (fp32) U H (fp32): G, H feed depthwise convs and carry the blocked fp32 residual streams (rows rounded up to 32)
     const size_t wide = e->cfg.enc ? 3 * D : (e->cfg.compute == ASRB_F32 ? 2 * D : 0);
     add(rows * wide * es);                                                  // qkv | fp32 GLU input
     add(e->cfg.enc ? rows * e->cfg.ffn * es : 0);                           // FFN hidden
@@ -247,8 +247,8 @@ EncBuffers carve(const asrb_encoder* e, int64_t B, int64_t T, void* ws, size_t w
     Arena a(ws, ws_bytes);
     EncBuffers b;
     b.a0 = a.take<char>(rows * (e->cfg.compute == ASRB_BF16 ? e->CP : e->cfg.mels) * es);
-    b.X = a.take<char>(rows * D * es); b.Y = a.take<char>(rows * D * es); b.G = a.take<char>(rows * D * 4);
-    b.U = a.take<char>(rows * D * es); b.H = a.take<char>(rows * D * 4);
+    b.X = a.take<char>(rows * D * es); b.Y = a.take<char>(rows * D * es); b.G = a.take<char>(res32_rows(rows) * D * 4);
+    b.U = a.take<char>(rows * D * es); b.H = a.take<char>(res32_rows(rows) * D * 4);
     const size_t wide = e->cfg.enc ? 3 * D : (e->cfg.compute == ASRB_F32 ? 2 * D : 0);
     b.wide = a.take<char>(rows * wide * es);
     b.ffn = a.take<char>(e->cfg.enc ? rows * e->cfg.ffn * es : 0);

@@ -249,7 +249,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     tmem_ld32(acc + c, v);
                     add_vec32(v, p.bias + gbase + c);
                     if (row_ok) {
-                        if (p.res32) add_f32x32(v, p.res32 + grow * p.N + gbase + c);
+                        if (p.res32) add_f32x32(v, p.res32, grow, gbase + c, p.N);
                         else if (p.res) add_res32(v, p.res + grow * p.N + gbase + c);
                     }
 #pragma unroll
@@ -278,7 +278,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     tmem_ld32(acc + c, v);
                     add_vec32(v, p.bias + gbase + c);
                     if (row_ok) {
-                        if (p.res32) add_f32x32(v, p.res32 + grow * p.N + gbase + c);
+                        if (p.res32) add_f32x32(v, p.res32, grow, gbase + c, p.N);
                         else if (p.res) add_res32(v, p.res + grow * p.N + gbase + c);
                     }
 #pragma unroll
@@ -290,7 +290,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         v[4 * i + 2] = fmaf((v[4 * i + 2] - mean) * rstd, gm.z, bt.z);
                         v[4 * i + 3] = fmaf((v[4 * i + 3] - mean) * rstd, gm.w, bt.w);
                     }
-                    if (p.out32 && row_ok) store_f32x32(p.out32 + grow * p.N + gbase + c, v);   // fp32 copy: the next residual stream
+                    if (p.out32 && row_ok) store_f32x32(p.out32, grow, gbase + c, p.N, v);   // fp32 copy: the next residual stream
                     const int cb = (c - c_begin) & 32;                        // which half of the 64-column staging tile
                     if (cb == 0) { if (leader) tma_wait_read0(); epi_bar(bar_id, 128); }
                     stage_store32(stg, r, cb, v, p.out_bf16 != 0);

@@ -119,13 +119,24 @@ __device__ __forceinline__ void add_res32(float (&v)[32], const op16* rp) {
         for (int j = 0; j < 4; ++j) { const float2 f = unpack_op16x2(h[j]); v[8 * i + 2 * j] += f.x; v[8 * i + 2 * j + 1] += f.y; }
     }
 }
-__device__ __forceinline__ void add_f32x32(float (&v)[32], const float* p) {     // plain (not read-only) loads
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { const float4 f = *(reinterpret_cast<const float4*>(p) + i); v[4 * i] += f.x; v[4 * i + 1] += f.y; v[4 * i + 2] += f.z; v[4 * i + 3] += f.w; }
+// ---- fp32 residual streams between kernels (workspace tensors, never user-visible) are stored in blocks of 32 rows,
+// [row / 32][column / 4][row % 32][4]: the LayerNorm epilogues own one ROW per thread, and with rows N floats apart a
+// warp's 16-byte access would touch 32 cache lines (the out-projection + LayerNorm launch of the TransformerEncoderLayer
+// spent 0.5 ms on L1 tag cycles for 0.1 TFLOP of MMAs); in this layout the 32 rows of a column group are 512 contiguous
+// bytes.  The channel-major producer (gemm_tct.cu, one CHANNEL per thread) writes 16-byte pieces, 8 sectors per warp store.
+// `rows` of such a tensor round up to a multiple of 32 (res32_rows, enc_kernels.cuh). ----
+__device__ __forceinline__ int64_t res32_index(int64_t row, int col, int N) {
+    return ((row >> 5) * (N >> 2) + (col >> 2)) * 128 + ((row & 31) << 2) + (col & 3);
 }
-__device__ __forceinline__ void store_f32x32(float* p, const float (&v)[32]) {
+__device__ __forceinline__ void add_f32x32(float (&v)[32], const float* base, int64_t row, int col, int N) {     // plain (not read-only) loads; col % 4 == 0
+    const float4* q = reinterpret_cast<const float4*>(base + res32_index(row, col, N));
 #pragma unroll
-    for (int i = 0; i < 8; ++i) *(reinterpret_cast<float4*>(p) + i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    for (int i = 0; i < 8; ++i) { const float4 f = q[32 * i]; v[4 * i] += f.x; v[4 * i + 1] += f.y; v[4 * i + 2] += f.z; v[4 * i + 3] += f.w; }
+}
+__device__ __forceinline__ void store_f32x32(float* base, int64_t row, int col, int N, const float (&v)[32]) {
+    float4* q = reinterpret_cast<float4*>(base + res32_index(row, col, N));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) q[32 * i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
 }
 __device__ __forceinline__ void add_vec32(float (&v)[32], const float* p) {
 #pragma unroll

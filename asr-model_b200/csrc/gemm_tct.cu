@@ -171,7 +171,7 @@ __device__ __forceinline__ void dw3_chunk(float (&v)[32], float& pa, float& pb, 
         }
         if (p.out32) {
 #pragma unroll
-            for (int jj = 0; jj < 16; ++jj) if (live(jj)) p.out32[eh + (int64_t)jj * ld] = o[jj];
+            for (int jj = 0; jj < 16; ++jj) if (live(jj)) p.out32[res32_index(row0 + tj + jj, c, ld)] = o[jj];   // blocked fp32 stream (gemm_tc_epi.cuh)
         }
         uint16_t* op = p.out + eh;
 #pragma unroll
