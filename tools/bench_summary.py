@@ -7,7 +7,8 @@ g = d['gemm_family']; print('family tflops', round(g['tflops'], 1), 'frac', roun
 f = d['front_end']; print('front end GB/s', round(f['achieved'], 1), 'frac', round(f['frac'], 4), 'ms', round(f['ms_per_step'], 4))
 w = d['whole_step']; print('whole tflops', round(w['tflops'], 1), 'sust', round(w['frac_sustained'], 4), 'burst', round(w['frac_burst'], 4))
 for k, v in d['kernels'].items(): print('  ', k, round(v['ms_per_step'], 4), round(v['share'], 3))
-print('cpu', round(d['cpu_baseline']['value'], 1), d['cpu_baseline']['cores'], 'cores; eager ms', d.get('gpu_eager_baseline', {}).get('fp32_tf32_ms_per_step'), d.get('gpu_eager_baseline', {}).get('bf16_autocast_ms_per_step'))
+cb = d.get('cpu_baseline') or {}
+print('cpu', cb.get('value'), cb.get('cores'), 'cores; eager ms', d.get('gpu_eager_baseline', {}).get('fp32_tf32_ms_per_step'), d.get('gpu_eager_baseline', {}).get('bf16_autocast_ms_per_step'))
 if 'enc1' in d: print('enc1', round(d['enc1']['ms_per_step'], 3), round(d['enc1']['frac_sustained'], 4))
 if 'ragged' in d: print('ragged', round(d['ragged']['ms_padding_encoded'], 3), round(d['ragged']['ms_padding_skipped'], 3))
 if 'attention_block' in d: print('attn', {k: round(v, 4) for k, v in d['attention_block'].items() if k != 'what'})
