@@ -17,7 +17,7 @@
 // spectra go to shared memory as [bin][frame] rows; the banded mel projection reads them back four frames at
 // a time (one LDS.128 + two FFMA2 per tap), then MUFU lg2.
 // The per-utterance dynamic-range floor (max - 8) needs the max of the WHOLE utterance, so this pass writes
-// (log10 + 4) / 4 and publishes the max with one atomicMax per block; logmel_floor_kernel then raises the
+// (log10 + 4) / 4 and every warp publishes its max (and the tile's min) with one reduction each; logmel_floor_kernel then raises the
 // values below the floor (monotone, so max((x+4)/4, (floor+4)/4) == (max(x, floor)+4)/4 bit for bit) and
 // only writes where something changes.
 #include "logmel.cuh"
@@ -112,8 +112,8 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 }
 
 // Persistent: gridDim.x blocks walk the (utterance, frame-tile) list; constants are staged once per block and the
-// PCM span of the NEXT tile streams in with cp.async (zero fill outside [0, len) = the center=True padding) while
-// the current tile is transformed.  HOP = 0: hop is a run-time value (no bank skew).
+// PCM span of the NEXT tile streams in under the mel stage -- TMA bulk copies for interior tiles, cp.async with zero fill
+// outside [0, len) (= the center=True padding) for the first / last tiles of an utterance.  HOP = 0: hop is a run-time value (no bank skew).
 template <int NFFT, int R, int FB, int HOP>
 __global__ void __launch_bounds__(LogmelCfg<NFFT, R, FB, HOP>::THREADS)
 logmel_kernel(const LogmelParams p, int tiles_per_utt, int total_tiles) {
